@@ -1,0 +1,168 @@
+/* vcd.h — C ABI of libvcd_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the hot path of olegroshka/vae-channel-dynamics: the SDXL
+ * AutoencoderKL training step + per-channel activation tracker + dead-channel
+ * classifier + GroupNorm-gamma nudge.  The reference has no FFI of its own: its
+ * interface is four Python modules.  Each entry point below
+ * names the reference call site (file:line under /root/reference) whose arithmetic
+ * it replaces; the Python host layer (vae-channel-dynamics_b200/src/...) keeps the
+ * reference's class/method names and reaches these symbols through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host
+ *   - activations are bf16, NHWC contiguous ([N][H][W][C]); statistics, GroupNorm
+ *     sums, loss accumulators and weight-gradient accumulators are fp32/fp64
+ *   - dtype codes: 0 = fp32, 1 = bf16
+ *   - no entry point allocates, synchronises the device, or touches a stream other
+ *     than `stream`; workspaces are caller-provided
+ *   - return 0 on success; otherwise a negative code and vcd_last_error() holds text
+ */
+#ifndef VCD_H_
+#define VCD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vcd_stream_t; /* cudaStream_t */
+
+#define VCD_F32 0
+#define VCD_BF16 1
+
+/* conv implementation selector */
+#define VCD_IMPL_AUTO 0 /* tcgen05 implicit GEMM when the shape allows, else SIMT direct */
+#define VCD_IMPL_SIMT 1 /* CUDA-core direct convolution (small-channel layers, cross-check) */
+#define VCD_IMPL_UMMA 2 /* tcgen05/TMEM/TMA implicit GEMM; error if the shape is unsupported */
+
+const char* vcd_last_error(void);
+int vcd_version(void);
+/* 1 if (Cin, Cout) can run on the tcgen05 implicit-GEMM path */
+int vcd_conv_umma_supported(int Cin, int Cout, int KH, int KW, int stride);
+
+/* ---- weights -------------------------------------------------------------------
+ * [upstream diffusers Conv2d/Linear parameters, OIHW] -> GEMM operand packs, redone
+ * after every optimizer step (train.py:302).
+ *   w_fprop : bf16 [KH*KW][Cout][Cin]   (K-major B operand of fprop)
+ *   w_dgrad : bf16 [KH*KW][Cin][Cout]   (K-major B operand of dgrad)   (may be NULL)
+ *   bias_f32: fp32 [Cout]                                              (may be NULL) */
+int vcd_pack_conv_weight(const void* w, const void* bias, int dtype, int Cout, int Cin, int KH, int KW,
+                         void* w_fprop, void* w_dgrad, float* bias_f32, vcd_stream_t stream);
+
+/* ---- convolution (AutoencoderKL.encode/decode conv layers; sdxl_vae_wrapper.py:60,71;
+ *      backward reached from train.py:299) ------------------------------------------
+ * y[n,ho,wo,co] = bias[co] + sum x[n, ho*stride - pad_t + kh, wo*stride - pad_l + kw, ci] * w[co,ci,kh,kw]
+ *                 (+ residual[n,ho,wo,co])
+ * Downsample2D's asymmetric (0,1,0,1) pad is pad_t = pad_l = 0 with Ho = H/2 (zero fill
+ * past the bottom/right edge).  x_planes != 0 (stride 2 only) means x is the parity-plane
+ * layout [N][2][2][H/2][W/2][C] written by vcd_space_to_planes. */
+int vcd_conv2d_fprop(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y,
+                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
+                     int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream);
+/* dx = conv_transpose(dy).  dx_planes != 0 (stride 2 only): dx is written in parity-plane layout. */
+int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void* w_dgrad, void* dx,
+                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
+                     int Ho, int Wo, int dx_planes, int impl, vcd_stream_t stream);
+/* dw (OIHW, `dtype`) and db ([Cout], `dtype`, may be NULL).  ws: fp32 workspace of
+ * vcd_conv2d_wgrad_ws_bytes() bytes (zeroed by the call). */
+int64_t vcd_conv2d_wgrad_ws_bytes(int Cin, int Cout, int KH, int KW);
+int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, int dtype, void* ws,
+                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
+                     int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream);
+
+/* NHWC [N][H][W][C] <-> parity planes [N][2][2][H/2][W/2][C] (stride-2 convs), H and W even */
+int vcd_space_to_planes(const void* x, void* xp, int N, int H, int W, int C, vcd_stream_t stream);
+int vcd_planes_to_space(const void* xp, void* x, int N, int H, int W, int C, vcd_stream_t stream);
+/* Upsample2D nearest x2 ([upstream] F.interpolate) and its adjoint (2x2 sum) */
+int vcd_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, vcd_stream_t stream);
+int vcd_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, vcd_stream_t stream);
+/* loader tensor (data_utils.py:28-29: fp32 NCHW in [-1,1]) -> bf16 NHWC, and back */
+int vcd_nchw_to_nhwc(const void* x, int x_dtype, void* y_bf16, int N, int C, int H, int W, vcd_stream_t stream);
+int vcd_nhwc_to_nchw(const void* x_bf16, void* y, int y_dtype, int N, int C, int H, int W, vcd_stream_t stream);
+int vcd_add(const void* a, const void* b, void* out, int64_t n, vcd_stream_t stream); /* bf16 */
+
+/* ---- GroupNorm(32, C, eps) [+ SiLU] with fused per-channel statistics -------------
+ * ([upstream] torch.nn.GroupNorm + F.silu inside ResnetBlock2D / Attention / conv_norm_out;
+ *  statistics: src/tracking/monitor.py:64-75)
+ * Pass 1  vcd_gn_stats      : sums[n][g] = {sum x, sum x^2} (fp64), optional per-channel
+ *                             statistics of the GroupNorm INPUT  (capture_point "input")
+ * Pass 2  vcd_gn_apply_fwd  : y = gamma*(x-mean)*rstd+beta ; optional statistics of y
+ *                             (capture_point "output", before SiLU) ; out = silu(y) if act
+ * chan stats layout (fp32 [5][C]): sum x, sum x^2, sum |x|, max |x|, count(|x| < near_zero)
+ * HW = H*W; x is [N][HW][C]. */
+int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, float near_zero,
+                 int N, int HW, int C, int G, vcd_stream_t stream);
+int vcd_gn_apply_fwd(const void* x, const double* sums, const void* gamma, const void* beta, int param_dtype,
+                     void* out, float* chan_stats_out, float near_zero, float eps, int act_silu,
+                     int N, int HW, int C, int G, vcd_stream_t stream);
+/* backward: dsdb[n][c] = {sum g*x, sum g} with g = dout * silu'(y) ; then dx; then dgamma/dbeta */
+int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
+                      int param_dtype, float* dsdb, float eps, int act_silu,
+                      int N, int HW, int C, int G, vcd_stream_t stream);
+int vcd_gn_bwd_apply(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
+                     int param_dtype, const float* dsdb, void* dx, float eps, int act_silu,
+                     int N, int HW, int C, int G, vcd_stream_t stream);
+int vcd_gn_param_grad(const double* sums, const float* dsdb, void* dgamma, void* dbeta, int param_dtype,
+                      float eps, int N, int HW, int C, int G, vcd_stream_t stream);
+/* stand-alone SiLU (only used when a foreign forward hook needs the pre-activation tensor) */
+int vcd_silu_fwd(const void* x, void* y, int64_t n, vcd_stream_t stream);
+int vcd_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, vcd_stream_t stream);
+
+/* ---- attention (mid_block.attentions.0; [upstream] AttnProcessor2_0, 1 head, d = C) ---
+ * GEMMs go through vcd_gemm_*; these are the row-softmax passes over S[N][T][T] (bf16). */
+int vcd_softmax_fwd(const void* s, void* p, int64_t rows, int cols, vcd_stream_t stream);
+int vcd_softmax_bwd(const void* p, const void* dp, void* ds, float scale, int64_t rows, int cols,
+                    vcd_stream_t stream);
+int vcd_transpose_bf16(const void* x, void* y, int batch, int rows, int cols, vcd_stream_t stream);
+/* D[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k] (+ bias[n]) (+ residual[b][m][n]); bf16 in/out,
+ * K-major operands (tcgen05); b_batch_stride_rows = 0 shares B across the batch (Linear). */
+int vcd_gemm_nt(const void* A, const void* B, const float* bias, const void* residual, void* D,
+                int batch, int M, int Nn, int K, int b_batched, float alpha, vcd_stream_t stream);
+/* D[b][m][n] = sum_k A[b][k][m] * B[b][k][n]  (both operands reduction-major; fp32 result via ws) */
+int vcd_gemm_tn(const void* A, const void* B, void* D, int d_dtype, void* ws_f32,
+                int batch, int M, int Nn, int K, int reduce_batch, vcd_stream_t stream);
+
+/* ---- latent distribution + losses -------------------------------------------------
+ * [upstream] DiagonalGaussianDistribution (sdxl_vae_wrapper.py:60-66) and train.py:289-291.
+ * moments: bf16 NHWC [N][hw][2*L]; eps_noise: fp32 NCHW-order [N][L][hw] (torch.randn order) or NULL (mode()).
+ * z: bf16 NHWC [N][hw][L]; kl_per_sample: fp32 [N] (zeroed by the call). */
+int vcd_gauss_sample_kl_fwd(const void* moments, const float* eps_noise, void* z, float* mean_out,
+                            float* logvar_out, float* kl_per_sample, int N, int hw, int L, vcd_stream_t stream);
+/* dmoments from dz (bf16 NHWC, may be NULL) and dkl (fp32 [N], may be NULL) */
+int vcd_gauss_sample_kl_bwd(const void* moments, const float* eps_noise, const void* dz, const float* dkl,
+                            void* dmoments, int N, int hw, int L, vcd_stream_t stream);
+/* mse: loss_sum (fp64, zeroed by the call) = sum (rec - x)^2 ; drec = 2*(rec-x)*grad_scale (bf16 NHWC).
+ * rec: bf16 NHWC; x: fp32 NCHW (the loader tensor, train.py:289). */
+int vcd_mse_fwd_bwd(const void* rec, const float* x_nchw, double* loss_sum, void* drec, float grad_scale,
+                    int N, int C, int H, int W, vcd_stream_t stream);
+
+/* ---- tracker / classifier / nudger / dead-weight scan -------------------------------
+ * vcd_chan_stats        : stand-alone per-channel statistics of any [N][HW][C] tensor
+ *                         (monitor.py:64-67 for non-GroupNorm targets such as encoder.conv_in)
+ * vcd_stats_finalize    : per-forward normalisation + running accumulation (monitor.py:101,
+ *                         176-186): run[0][c] += sumabs/Nf, run[1][c] += mean_c, run[2][c] += var_c,
+ *                         run[3][c] = max(.., maxabs), run[4][c] += nearzero/Nf;
+ *                         scal[0] += mean_activation, scal[1] += std_activation (unbiased), scal[2] += 1
+ *                         (forward count); then chan_stats is zeroed for the next forward
+ * vcd_classify_mask     : mask[c] = mean_abs[c] < thr (strict, fp32; classifier.py:135), count
+ * vcd_nudge_gamma       : gamma[idx] = min(gamma*factor, cap) in fp64, RN to dtype (nudger.py:127-143);
+ *                         mode 1 = reset to 1.0 (nudger.py:162-168); out-of-range indices skipped;
+ *                         applied_count (int32, device) receives the number applied
+ * vcd_dead_weight_count : for T tensors, count |w| < thr and/or |w| < pct*mean|w| (deadneuron.py:78-115) */
+int vcd_chan_stats(const void* x, int x_dtype, float* chan_stats, float near_zero, int N, int HW, int C,
+                   int channels_last, vcd_stream_t stream);
+int vcd_stats_finalize(float* chan_stats, float* run, double* scal, int64_t n_per_channel, int C,
+                       vcd_stream_t stream);
+int vcd_classify_mask(const float* mean_abs, float threshold, uint8_t* mask, int32_t* count, int C,
+                      vcd_stream_t stream);
+int vcd_nudge_gamma(void* gamma, int dtype, int C, const int64_t* idx, int n_idx, double factor, double cap,
+                    int mode, int32_t* applied_count, vcd_stream_t stream);
+int vcd_dead_weight_count(const void* const* tensors, const int64_t* numels, const int32_t* dtypes, int T,
+                          double threshold, double mean_percentage, int dead_type, double* sum_abs_ws,
+                          int64_t* counts, vcd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCD_H_ */

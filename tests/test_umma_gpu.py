@@ -1,0 +1,96 @@
+"""tcgen05 implicit-GEMM kernel (umma_gemm.cu) parity: against torch fp32 conv/matmul on bf16-rounded
+inputs AND against the independent CUDA-core kernels.  Shapes cover every layer class of the SDXL VAE
+(SURVEY 8a5.1): 128/256/512 channels, 3x3 s1, 3x3 s2 with (0,1,0,1) pad, 1x1 shortcuts, Linear,
+ragged tiles (W not a multiple of the tile, batch not a multiple of the tile)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_kernels_gpu import _conv_case
+from util import bf16_round, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(1)
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,stride", [
+    (2, 16, 16, 128, 128, 3, 1),
+    (1, 8, 8, 128, 128, 3, 1),      # 64 pixels: tile spans a missing second image
+    (3, 8, 8, 512, 512, 3, 1),      # odd batch, BLOCK_N 256, 2 n-tiles
+    (2, 32, 32, 128, 256, 3, 1),
+    (1, 16, 16, 256, 128, 1, 1),    # 1x1 shortcut
+    (2, 12, 20, 128, 128, 3, 1),    # ragged: W, H not powers of two
+    (1, 6, 136, 128, 128, 3, 1),    # W > 128 with a partial tile
+    (2, 16, 16, 128, 128, 3, 2),    # Downsample2D
+    (1, 32, 32, 256, 256, 3, 2),
+])
+def test_conv_umma(vcd, N, H, W, cin, cout, k, stride):
+    _conv_case(vcd, N, H, W, cin, cout, k, stride, vcd._lib.IMPL_UMMA)
+
+
+def test_conv_umma_residual(vcd):
+    _conv_case(vcd, 2, 16, 16, 256, 256, 3, 1, vcd._lib.IMPL_UMMA, residual=True)
+
+
+def test_conv_umma_matches_simt_bitwise_close(vcd):
+    """same bf16 inputs through both device paths: only fp32 summation order differs."""
+    ops = vcd.ops
+    x = torch.randn(2, 16, 16, 128, device="cuda").to(torch.bfloat16)
+    w = torch.randn(128, 128, 3, 3, device="cuda") / 34.0
+    b = torch.randn(128, device="cuda")
+    ya = ops.conv2d(x, w, b, ops.PackedWeights(), impl=vcd._lib.IMPL_UMMA)
+    yb = ops.conv2d(x, w, b, ops.PackedWeights(), impl=vcd._lib.IMPL_SIMT)
+    assert rel_err(ya, yb) < 4e-3
+
+
+@pytest.mark.parametrize("batch,M,N,K,bb", [(1, 256, 512, 512, False), (3, 64, 64, 512, True), (2, 200, 128, 64, True),
+                                            (2, 4096, 512, 512, False)])
+def test_gemm_nt(vcd, batch, M, N, K, bb):
+    ops = vcd.ops
+    A = torch.randn(batch, M, K, device="cuda").to(torch.bfloat16)
+    B = (torch.randn(batch if bb else 1, N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(batch, M, N, device="cuda").to(torch.bfloat16)
+    D = torch.empty(batch, M, N, dtype=torch.bfloat16, device="cuda")
+    ops._gemm_nt(A, B, D, batch, M, N, K, bb, alpha=0.5, bias=bias, residual=res)
+    ref = 0.5 * torch.matmul(A.float(), B.float().transpose(1, 2)) + bias + res.float()
+    assert rel_err(D, ref) < TOL
+
+
+@pytest.mark.parametrize("batch,M,N,K,red", [(2, 128, 512, 256, False), (3, 64, 512, 64, False), (2, 512, 512, 1000, True),
+                                             (1, 256, 128, 64, True)])
+def test_gemm_tn(vcd, batch, M, N, K, red):
+    ops = vcd.ops
+    A = torch.randn(batch, K, M, device="cuda").to(torch.bfloat16)
+    B = (torch.randn(batch, K, N, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+    nb = 1 if red else batch
+    D = torch.empty(nb, M, N, dtype=torch.float32, device="cuda")
+    ops._gemm_tn(A, B, D, batch, M, N, K, red)
+    ref = torch.matmul(A.float().transpose(1, 2), B.float())
+    if red:
+        ref = ref.sum(0, keepdim=True)
+    assert rel_err(D, ref) < TOL
+
+
+@pytest.mark.parametrize("T", [64, 256, 1024])
+def test_attention_core(vcd, T):
+    ops = vcd.ops
+    N, C = 2, 512
+    q, k, v = [bf16_round(torch.randn(N, T, C, device="cuda")) for _ in range(3)]
+    qr, kr, vr = [t.clone().requires_grad_() for t in (q, k, v)]
+    ref = torch.softmax(qr @ kr.transpose(1, 2) / math.sqrt(C), -1) @ vr
+    qp, kp, vp = [t.to(torch.bfloat16).requires_grad_() for t in (q, k, v)]
+    o = ops.attention_core(qp, kp, vp)
+    assert rel_err(o, ref) < 2e-2
+    g = bf16_round(torch.randn_like(ref))
+    ref.backward(g)
+    o.backward(g.to(torch.bfloat16))
+    for a, b in ((qp, qr), (kp, kr), (vp, vr)):
+        assert rel_err(a.grad, b.grad) < 3e-2

@@ -1,0 +1,13 @@
+// conv_dispatch.h — internal (non-ABI) entry points shared between conv_simt.cu and conv_dispatch.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+int simt_conv_fprop(const void* x, const void* wf, const float* bias, const void* residual, void* y, int N, int H, int W,
+                    int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, cudaStream_t st);
+int simt_conv_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                    int stride, int pad_t, int pad_l, int Ho, int Wo, cudaStream_t st);
+int simt_conv_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                    int stride, int pad_t, int pad_l, int Ho, int Wo, cudaStream_t st);
+int conv_bias_grad(const void* dy, float* out, int64_t pixels, int C, cudaStream_t st);
+int conv_wgrad_finalize(const float* ws, void* dw, void* db, int dtype, int Cout, int Cin, int taps, cudaStream_t st);

@@ -1,0 +1,368 @@
+// gn.cu — GroupNorm(32,C,eps)[+SiLU] forward/backward on bf16 NHWC with fused per-channel
+// activation statistics (HBM-bound kernels; 16-byte vector access, fp32 math).
+//
+// Replaces [upstream] torch.nn.GroupNorm + F.silu reached from sdxl_vae_wrapper.py:60,71 and the
+// hook arithmetic of src/tracking/monitor.py:64-75 (|t|.mean(dim=[0,2,3]) etc.), which in the
+// reference is a second full read of the tensor plus a blocking D2H per hook.
+//
+// Thread mapping (all kernels): a pixel row of C channels is V = C/8 16-byte vectors; a 256-thread
+// block covers PL = 256/V pixels per iteration; thread (pl, v) walks pixels pl, pl+PL, ... of its
+// block's pixel range inside ONE image (blockIdx.y = n), so every warp reads contiguous 512 B.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kIters = 32;  // pixels per thread per block
+
+struct Map {
+  int V, PL, v, pl, c0;
+  int64_t p_begin, p_end;
+};
+__device__ __forceinline__ Map make_map(int C, int HW) {
+  Map m;
+  m.V = C >> 3;
+  m.PL = kThreads / m.V;
+  m.v = threadIdx.x % m.V;
+  m.pl = threadIdx.x / m.V;
+  m.c0 = m.v * 8;
+  int64_t ppb = (int64_t)m.PL * kIters;
+  m.p_begin = (int64_t)blockIdx.x * ppb;
+  m.p_end = min(m.p_begin + ppb, (int64_t)HW);
+  return m;
+}
+
+__device__ __forceinline__ void group_mean_rstd(const double* sums, int n, int G, int g, double cnt, float eps,
+                                                float& mean, float& rstd) {
+  double s = sums[((int64_t)n * G + g) * 2], q = sums[((int64_t)n * G + g) * 2 + 1];
+  double mu = s / cnt;
+  double var = q / cnt - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean = (float)mu;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---------------------------------------------------------------- pass 1: group sums (+ input stats)
+template <bool STATS>
+__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ sums,
+                                                            float* __restrict__ cstats, float near_zero, int HW,
+                                                            int C, int G) {
+  extern __shared__ float sm[];  // [C][2] (+ [C][3] when STATS: sumabs, max, nz)
+  const int n = blockIdx.y;
+  Map m = make_map(C, HW);
+  for (int i = threadIdx.x; i < C * (STATS ? 5 : 2); i += kThreads) sm[i] = 0.f;
+  __syncthreads();
+  float s[8], q[8], sa[8], mx[8], nz[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0.f;
+  const bf16* xb = x + (int64_t)n * HW * C + m.c0;
+  for (int64_t p = m.p_begin + m.pl; p < m.p_end; p += m.PL) {
+    float f[8];
+    unpack8(ld8(xb + p * C), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      q[j] += f[j] * f[j];
+      if (STATS) {
+        float a = fabsf(f[j]);
+        sa[j] += a;
+        mx[j] = fmaxf(mx[j], a);
+        nz[j] += (a < near_zero) ? 1.f : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm[(m.c0 + j) * 2], s[j]);
+    atomicAdd(&sm[(m.c0 + j) * 2 + 1], q[j]);
+    if (STATS) {
+      atomicAdd(&sm[2 * C + (m.c0 + j) * 3], sa[j]);
+      atomic_max_nonneg(&sm[2 * C + (m.c0 + j) * 3 + 1], mx[j]);
+      atomicAdd(&sm[2 * C + (m.c0 + j) * 3 + 2], nz[j]);
+    }
+  }
+  __syncthreads();
+  const int D = C / G;
+  for (int g = threadIdx.x; g < G; g += kThreads) {
+    double gs = 0.0, gq = 0.0;
+    for (int j = 0; j < D; ++j) {
+      gs += (double)sm[(g * D + j) * 2];
+      gq += (double)sm[(g * D + j) * 2 + 1];
+    }
+    atomicAdd(&sums[((int64_t)n * G + g) * 2], gs);
+    atomicAdd(&sums[((int64_t)n * G + g) * 2 + 1], gq);
+  }
+  if (STATS) {
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      atomicAdd(&cstats[0 * C + c], sm[c * 2]);
+      atomicAdd(&cstats[1 * C + c], sm[c * 2 + 1]);
+      atomicAdd(&cstats[2 * C + c], sm[2 * C + c * 3]);
+      atomic_max_nonneg(&cstats[3 * C + c], sm[2 * C + c * 3 + 1]);
+      atomicAdd(&cstats[4 * C + c], sm[2 * C + c * 3 + 2]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- pass 2: normalise (+ output stats, SiLU)
+template <bool STATS>
+__global__ void __launch_bounds__(kThreads) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ sums,
+                                                            const void* __restrict__ gamma, const void* __restrict__ beta,
+                                                            int pdt, bf16* __restrict__ out, float* __restrict__ cstats,
+                                                            float near_zero, float eps, int act, int HW, int C, int G) {
+  extern __shared__ float sm[];  // [C][5] when STATS
+  const int n = blockIdx.y;
+  Map m = make_map(C, HW);
+  if (STATS) {
+    for (int i = threadIdx.x; i < C * 5; i += kThreads) sm[i] = 0.f;
+    __syncthreads();
+  }
+  const int D = C / G;
+  const double cnt = (double)D * (double)HW;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = m.c0 + j;
+    float mean, rstd;
+    group_mean_rstd(sums, n, G, c / D, cnt, eps, mean, rstd);
+    a[j] = rstd * load_param(gamma, pdt, c);
+    b[j] = load_param(beta, pdt, c) - mean * a[j];
+  }
+  float s[8], q[8], sa[8], mx[8], nz[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0.f;
+  const int64_t base = (int64_t)n * HW * C + m.c0;
+  for (int64_t p = m.p_begin + m.pl; p < m.p_end; p += m.PL) {
+    float f[8];
+    unpack8(ld8(x + base + p * C), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(a[j], f[j], b[j]);
+      if (STATS) {
+        float ab = fabsf(y);
+        s[j] += y;
+        q[j] += y * y;
+        sa[j] += ab;
+        mx[j] = fmaxf(mx[j], ab);
+        nz[j] += (ab < near_zero) ? 1.f : 0.f;
+      }
+      f[j] = act ? silu_f(y) : y;
+    }
+    st8(out + base + p * C, pack8(f));
+  }
+  if (STATS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = m.c0 + j;
+      atomicAdd(&sm[c * 5 + 0], s[j]);
+      atomicAdd(&sm[c * 5 + 1], q[j]);
+      atomicAdd(&sm[c * 5 + 2], sa[j]);
+      atomic_max_nonneg(&sm[c * 5 + 3], mx[j]);
+      atomicAdd(&sm[c * 5 + 4], nz[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      atomicAdd(&cstats[0 * C + c], sm[c * 5 + 0]);
+      atomicAdd(&cstats[1 * C + c], sm[c * 5 + 1]);
+      atomicAdd(&cstats[2 * C + c], sm[c * 5 + 2]);
+      atomic_max_nonneg(&cstats[3 * C + c], sm[c * 5 + 3]);
+      atomicAdd(&cstats[4 * C + c], sm[c * 5 + 4]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward pass 1: ds/db per (n, c)
+__global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
+                                                                 const double* __restrict__ sums,
+                                                                 const void* __restrict__ gamma,
+                                                                 const void* __restrict__ beta, int pdt,
+                                                                 float* __restrict__ dsdb, float eps, int act, int HW,
+                                                                 int C, int G) {
+  extern __shared__ float sm[];  // [C][2]
+  const int n = blockIdx.y;
+  Map m = make_map(C, HW);
+  for (int i = threadIdx.x; i < C * 2; i += kThreads) sm[i] = 0.f;
+  __syncthreads();
+  const int D = C / G;
+  const double cnt = (double)D * (double)HW;
+  float a[8], b[8], ds[8], db[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = m.c0 + j;
+    float mean, rstd;
+    group_mean_rstd(sums, n, G, c / D, cnt, eps, mean, rstd);
+    a[j] = rstd * load_param(gamma, pdt, c);
+    b[j] = load_param(beta, pdt, c) - mean * a[j];
+    ds[j] = db[j] = 0.f;
+  }
+  const int64_t base = (int64_t)n * HW * C + m.c0;
+  for (int64_t p = m.p_begin + m.pl; p < m.p_end; p += m.PL) {
+    float f[8], g[8];
+    unpack8(ld8(x + base + p * C), f);
+    unpack8(ld8(dout + base + p * C), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float gg = g[j];
+      if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
+      ds[j] += gg * f[j];
+      db[j] += gg;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm[(m.c0 + j) * 2], ds[j]);
+    atomicAdd(&sm[(m.c0 + j) * 2 + 1], db[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += kThreads) atomicAdd(&dsdb[(int64_t)n * C * 2 + i], sm[i]);
+}
+
+// ---------------------------------------------------------------- backward pass 2: dx
+__global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
+                                                                const double* __restrict__ sums,
+                                                                const void* __restrict__ gamma,
+                                                                const void* __restrict__ beta, int pdt,
+                                                                const float* __restrict__ dsdb, bf16* __restrict__ dx,
+                                                                float eps, int act, int HW, int C, int G) {
+  const int n = blockIdx.y;
+  Map m = make_map(C, HW);
+  const int D = C / G;
+  const double cnt = (double)D * (double)HW;
+  float a[8], b[8], c2[8], c3[8];
+  int prev_g = -1;
+  float pc2 = 0.f, pc3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = m.c0 + j;
+    int g = c / D;
+    float mean, rstd;
+    group_mean_rstd(sums, n, G, g, cnt, eps, mean, rstd);
+    a[j] = rstd * load_param(gamma, pdt, c);
+    b[j] = load_param(beta, pdt, c) - mean * a[j];
+    if (g != prev_g) {
+      float S1 = 0.f, S2 = 0.f;
+      for (int k = 0; k < D; ++k) {
+        int cc = g * D + k;
+        float gm = load_param(gamma, pdt, cc);
+        S1 += gm * dsdb[((int64_t)n * C + cc) * 2];
+        S2 += gm * dsdb[((int64_t)n * C + cc) * 2 + 1];
+      }
+      float inv = 1.f / (float)cnt;
+      pc2 = (S2 * mean - S1) * rstd * rstd * rstd * inv;
+      pc3 = -pc2 * mean - S2 * rstd * inv;
+      prev_g = g;
+    }
+    c2[j] = pc2;
+    c3[j] = pc3;
+  }
+  const int64_t base = (int64_t)n * HW * C + m.c0;
+  for (int64_t p = m.p_begin + m.pl; p < m.p_end; p += m.PL) {
+    float f[8], g[8];
+    unpack8(ld8(x + base + p * C), f);
+    unpack8(ld8(dout + base + p * C), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float gg = g[j];
+      if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
+      g[j] = fmaf(a[j], gg, fmaf(c2[j], f[j], c3[j]));
+    }
+    st8(dx + base + p * C, pack8(g));
+  }
+}
+
+__global__ void gn_param_grad_kernel(const double* __restrict__ sums, const float* __restrict__ dsdb, void* dgamma,
+                                     void* dbeta, int pdt, float eps, int N, int HW, int C, int G) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int D = C / G;
+  const double cnt = (double)D * (double)HW;
+  float dg = 0.f, dbv = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float mean, rstd;
+    group_mean_rstd(sums, n, G, c / D, cnt, eps, mean, rstd);
+    float ds = dsdb[((int64_t)n * C + c) * 2], db = dsdb[((int64_t)n * C + c) * 2 + 1];
+    dg += (ds - mean * db) * rstd;
+    dbv += db;
+  }
+  store_param(dgamma, pdt, c, dg);
+  store_param(dbeta, pdt, c, dbv);
+}
+
+int check_shape(int C, int G) {
+  int V = C / 8;
+  if (C % 8 != 0 || V < 1 || V > kThreads || (kThreads % V) != 0) {
+    vcd_set_error("GroupNorm kernels need C %% 8 == 0 and C/8 a divisor of 256 (got C=%d)", C);
+    return -1;
+  }
+  if (G <= 0 || C % G != 0) {
+    vcd_set_error("GroupNorm: C=%d not divisible by G=%d", C, G);
+    return -1;
+  }
+  return 0;
+}
+dim3 gn_grid(int N, int HW, int C) {
+  int PL = kThreads / (C / 8);
+  return dim3((unsigned)ceil_div64(HW, (int64_t)PL * kIters), (unsigned)N);
+}
+
+}  // namespace
+
+extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, float near_zero, int N, int HW, int C,
+                            int G, vcd_stream_t stream) {
+  if (check_shape(C, G)) return -1;
+  cudaStream_t st = as_stream(stream);
+  VCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * G, st));
+  if (chan_stats_in)
+    gn_stats_kernel<true><<<gn_grid(N, HW, C), kThreads, C * 5 * sizeof(float), st>>>((const bf16*)x, sums, chan_stats_in,
+                                                                                     near_zero, HW, C, G);
+  else
+    gn_stats_kernel<false><<<gn_grid(N, HW, C), kThreads, C * 2 * sizeof(float), st>>>((const bf16*)x, sums, nullptr,
+                                                                                      near_zero, HW, C, G);
+  VCD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vcd_gn_apply_fwd(const void* x, const double* sums, const void* gamma, const void* beta, int param_dtype,
+                                void* out, float* chan_stats_out, float near_zero, float eps, int act_silu, int N,
+                                int HW, int C, int G, vcd_stream_t stream) {
+  if (check_shape(C, G)) return -1;
+  cudaStream_t st = as_stream(stream);
+  if (chan_stats_out)
+    gn_apply_kernel<true><<<gn_grid(N, HW, C), kThreads, C * 5 * sizeof(float), st>>>(
+        (const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, chan_stats_out, near_zero, eps, act_silu, HW, C, G);
+  else
+    gn_apply_kernel<false><<<gn_grid(N, HW, C), kThreads, 0, st>>>((const bf16*)x, sums, gamma, beta, param_dtype,
+                                                                   (bf16*)out, nullptr, near_zero, eps, act_silu, HW, C, G);
+  VCD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
+                                 int param_dtype, float* dsdb, float eps, int act_silu, int N, int HW, int C, int G,
+                                 vcd_stream_t stream) {
+  if (check_shape(C, G)) return -1;
+  cudaStream_t st = as_stream(stream);
+  VCD_CUDA(cudaMemsetAsync(dsdb, 0, sizeof(float) * 2 * N * C, st));
+  gn_bwd_reduce_kernel<<<gn_grid(N, HW, C), kThreads, C * 2 * sizeof(float), st>>>(
+      (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, eps, act_silu, HW, C, G);
+  VCD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
+                                int param_dtype, const float* dsdb, void* dx, float eps, int act_silu, int N, int HW,
+                                int C, int G, vcd_stream_t stream) {
+  if (check_shape(C, G)) return -1;
+  gn_bwd_apply_kernel<<<gn_grid(N, HW, C), kThreads, 0, as_stream(stream)>>>(
+      (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, eps, act_silu, HW, C, G);
+  VCD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vcd_gn_param_grad(const double* sums, const float* dsdb, void* dgamma, void* dbeta, int param_dtype,
+                                 float eps, int N, int HW, int C, int G, vcd_stream_t stream) {
+  if (check_shape(C, G)) return -1;
+  gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(sums, dsdb, dgamma, dbeta, param_dtype, eps, N, HW,
+                                                                       C, G);
+  VCD_LAUNCH_CHECK();
+  return 0;
+}

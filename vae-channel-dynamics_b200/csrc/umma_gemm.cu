@@ -1,0 +1,406 @@
+// umma_gemm.cu — persistent, warp-specialised tcgen05 implicit-GEMM kernel for sm_100a.
+//
+//   warp 0 (1 lane)  : TMA producer  — cp.async.bulk.tensor.5d into a ring of 128B-swizzled stages
+//   warp 1 (1 lane)  : MMA issuer    — tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM,
+//                                      tcgen05.commit releases stages / publishes accumulators
+//   warp 2           : TMEM allocator (tcgen05.alloc / dealloc)
+//   warps 4..7       : epilogue      — tcgen05.ld (each warp its own 32 TMEM lanes) -> bias/residual/
+//                                      bf16 pack -> global (form 0) or red.global.add.f32 (form 1)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// See umma_gemm.cuh for the two operand forms.  Reference arithmetic replaced: the cuDNN/cuBLAS calls
+// behind diffusers' Conv2d/Linear/attention, reached from sdxl_vae_wrapper.py:60,71 and
+// train.py:299.
+#include "umma_gemm.cuh"
+
+namespace {
+
+constexpr int kStageA = 16384;  // 128 rows x 128 B (form 0) or 2 boxes of 64 x 128 B (form 1)
+constexpr int kThreads = 256;
+constexpr long long kSpinLimit = 4000000000LL;  // ~2 s at 2 GHz: turn a deadlock into a trap
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kSpinLimit) {
+      printf("vcd umma_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct PixTile {
+  int w0, h0, n0;
+};
+__device__ __forceinline__ PixTile decode_pix(const UmmaParams& p, int t) {
+  PixTile r;
+  int tw = t % p.tiles_w;
+  int q = t / p.tiles_w;
+  r.w0 = tw * p.tile_w;
+  r.h0 = (q % p.tiles_h) * p.tile_h;
+  r.n0 = (q / p.tiles_h) * p.tile_n;
+  return r;
+}
+
+// form-1 tile -> (batch, tap, m tile, n tile, first K step, K steps)
+struct RedTile {
+  int batch, tap, mt, nt, k0, nk;
+};
+__device__ __forceinline__ RedTile decode_red(const UmmaParams& p, int t) {
+  RedTile r;
+  int split = t % p.splits;
+  int q = t / p.splits;
+  r.nt = q % p.n_tiles;
+  q /= p.n_tiles;
+  r.mt = q % p.m_tiles;
+  q /= p.m_tiles;
+  r.tap = q % p.ntaps;
+  r.batch = q / p.ntaps;
+  r.k0 = split * p.k_per_split;
+  int k1 = min(r.k0 + p.k_per_split, p.k_tiles);
+  r.nk = k1 - r.k0;
+  return r;
+}
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kStageB = BLOCK_N * 128;
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ UmmaParams p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ============================== TMA producer ==============================
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (p.form == 0) {
+        const int nt = tile % p.n_tiles;
+        const PixTile pt = decode_pix(p, tile / p.n_tiles);
+        const int brow0 = nt * BLOCK_N + pt.n0 * p.b_batch_rows;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * C::kStageBytes;
+            mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+            tma_load_5d(sa, &mapA, full_bar(stage), kc * 64, pt.w0 + p.tap_dw[tap], pt.h0 + p.tap_dh[tap],
+                        p.tap_plane[tap], pt.n0);
+            tma_load_5d(sa + kStageA, &mapB, full_bar(stage), kc * 64, brow0 + p.tap_brow[tap], 0, 0, 0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else {
+        const RedTile rt = decode_red(p, tile);
+        const int tiles_per_img = p.tiles_w * p.tiles_h;
+        for (int k = 0; k < rt.nk; ++k) {
+          // batched (attention): pixel tiles of image `batch` only; conv wgrad: all pixel tiles
+          const int pix = (p.batches > 1 ? rt.batch * tiles_per_img : 0) + rt.k0 + k;
+          const PixTile pt = decode_pix(p, pix);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, pt.w0, pt.h0, 0, pt.n0);
+#pragma unroll
+          for (int b = 0; b < BLOCK_N / 64; ++b)
+            tma_load_5d(sa + kStageA + b * 8192, &mapB, full_bar(stage), rt.nt * BLOCK_N + b * 64,
+                        pt.w0 + p.tap_dw[rt.tap], pt.h0 + p.tap_dh[rt.tap], p.tap_plane[rt.tap], pt.n0);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ============================== MMA issuer ==============================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nk;
+      if (p.form == 0) nk = p.ntaps * p.kc_per_tap;
+      else nk = decode_red(p, tile).nk;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int k = 0; k < nk; ++k) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::kStageBytes;
+        const uint32_t sb = sa + kStageA;
+        uint64_t adesc = ((uint64_t)p.a_desc_hi << 32) | (uint64_t)(((sa >> 4) & 0x3FFFu) | (p.a_lbo << 16));
+        uint64_t bdesc = ((uint64_t)p.b_desc_hi << 32) | (uint64_t)(((sb >> 4) & 0x3FFFu) | (p.b_lbo << 16));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          umma_bf16(d_tmem, adesc, bdesc, p.idesc, (k | j) != 0 ? 1u : 0u);
+          adesc += p.a_kstep;
+          bdesc += p.b_kstep;
+        }
+        umma_commit(empty_bar(stage));  // stage reusable once these MMAs have read it
+        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(acc));  // accumulator complete
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue ==============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      if (p.form == 0) {
+        const int nt = tile % p.n_tiles;
+        const PixTile pt = decode_pix(p, tile / p.n_tiles);
+        const int wi = row % p.tile_w;
+        const int rq = row / p.tile_w;
+        const int hi = rq % p.tile_h;
+        const int ni = rq / p.tile_h;
+        const int w = pt.w0 + wi, h = pt.h0 + hi, n = pt.n0 + ni;
+        const bool valid = (w < p.W) && (h < p.H) && (n < p.Nimg);
+        const long long off = (long long)n * p.out_sn + (long long)h * p.out_sh + (long long)w * p.out_sw + nt * BLOCK_N;
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_wait_ld();
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            if (p.bias) {
+              const float* bp = p.bias + nt * BLOCK_N + ch * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nt * BLOCK_N + ch * 32 + j < p.Nout) v[j] += __ldg(bp + j);
+            }
+            if (p.residual) {
+              const bf16* rp = p.residual + off + ch * 32;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float f[8];
+                if (nt * BLOCK_N + ch * 32 + g * 8 >= p.Nout) continue;
+                unpack8(ld8(rp + g * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+              }
+            }
+            bf16* op = p.out + off + ch * 32;
+            const int col0 = nt * BLOCK_N + ch * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (col0 + g * 8 < p.Nout) st8(op + g * 8, pack8(v + g * 8));
+          }
+        }
+      } else {
+        const RedTile rt = decode_red(p, tile);
+        float* op = p.acc +
+                    (((long long)rt.batch * p.ntaps + rt.tap) * p.Mout + rt.mt * 128 + row) * (long long)p.Nout +
+                    rt.nt * BLOCK_N;
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_wait_ld();
+          if (rt.mt * 128 + row < p.Mout) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (rt.nt * BLOCK_N + ch * 32 + j < p.Nout) atomicAdd(op + ch * 32 + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+
+int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int P, int N, int box_c, int box_w, int box_h,
+                 int box_n) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    vcd_set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+    return -4;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)P, (cuuint64_t)N};
+  cuuint64_t s1 = (cuuint64_t)C * 2, s2 = s1 * W, s3 = s2 * H, s4 = s3 * P;
+  cuuint64_t strides[4] = {s1, s2, s3, s4};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u, (cuuint32_t)box_n};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (s1 & 15)) {
+    vcd_set_error("TMA map: base/stride not 16-byte aligned (C=%d)", C);
+    return -4;
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vcd_set_error("cuTensorMapEncodeTiled failed (%d) dims=(%d,%d,%d,%d,%d) box=(%d,%d,%d,1,%d)", (int)r, C, W, H, P, N,
+                  box_c, box_w, box_h, box_n);
+    return -4;
+  }
+  return 0;
+}
+
+int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p, int block_n, cudaStream_t st) {
+  int grid = p.total_tiles < vcd_num_sms() ? p.total_tiles : vcd_num_sms();
+  if (grid <= 0) return 0;
+  if (block_n == 256) {
+    static bool attr = false;
+    if (!attr) {
+      VCD_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<256>::kSmemBytes));
+      attr = true;
+    }
+    umma_gemm_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(mapA, mapB, p);
+  } else if (block_n == 128) {
+    static bool attr = false;
+    if (!attr) {
+      VCD_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<128>::kSmemBytes));
+      attr = true;
+    }
+    umma_gemm_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(mapA, mapB, p);
+  } else {
+    vcd_set_error("umma_launch: BLOCK_N %d unsupported", block_n);
+    return -1;
+  }
+  VCD_LAUNCH_CHECK();
+  return 0;
+}

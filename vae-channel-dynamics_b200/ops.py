@@ -1,0 +1,496 @@
+"""Autograd bindings of the libvcd_b200 kernels.
+
+Internal activation layout: bf16, NHWC contiguous tensors of shape [N, H, W, C].  Parameters stay
+ordinary ``nn.Parameter``s (fp32 or bf16, diffusers OIHW layout) so the optimizer, DDP, the nudger
+and the dead-weight tracker all see the storage they see in the reference; GEMM operand packs are
+rebuilt from them whenever ``param._version`` changes (i.e. after every optimizer step / nudge).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, IMPL_AUTO, IMPL_SIMT, IMPL_UMMA, call
+
+_conv_impl = IMPL_AUTO
+
+
+def set_conv_impl(impl: int) -> None:
+    """IMPL_AUTO (default), IMPL_SIMT (CUDA-core cross-check) or IMPL_UMMA."""
+    global _conv_impl
+    _conv_impl = impl
+
+
+def get_conv_impl() -> int:
+    return _conv_impl
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise _lib.VcdError(f"unsupported parameter dtype {t.dtype} (fp32 and bf16 only; fp16 is not a meaningful "
+                        "target, SURVEY appendix A.10)")
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise _lib.VcdError(f"{what} must live on a CUDA device: the hot path has no CPU implementation")
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.bfloat16:
+        raise _lib.VcdError(f"internal activations are bf16, got {x.dtype}")
+    return x if x.is_contiguous() else x.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# statistics slots (device side of ActivityMonitor)
+# ------------------------------------------------------------------------------------------
+class TrackSlot:
+    """Per (layer, capture point) device accumulators.
+
+    raw  fp32 [5][C] : sums of ONE forward (sum, sum^2, sum|x|, max|x|, #near-zero), zeroed by finalize
+    run  fp32 [5][C] : sum over forwards of per-forward (mean|x|, mean, var, max, near-zero fraction)
+    scal fp64 [3]    : sum of per-forward mean_activation, std_activation, forward count
+    """
+
+    def __init__(self, channels: int, device, near_zero: float = 0.0):
+        self.C = channels
+        self.near_zero = float(near_zero)
+        self.raw = torch.zeros(5 * channels, dtype=torch.float32, device=device)
+        self.run = torch.zeros(5 * channels, dtype=torch.float32, device=device)
+        self.scal = torch.zeros(3, dtype=torch.float64, device=device)
+
+    def finalize(self, n_per_channel: int) -> None:
+        call("vcd_stats_finalize", _p(self.raw), _p(self.run), _p(self.scal), int(n_per_channel), self.C, _st())
+
+    def reset(self) -> None:
+        self.run.zero_()
+        self.scal.zero_()
+        self.raw.zero_()
+
+
+def chan_stats(x: torch.Tensor, slot: TrackSlot) -> None:
+    """Stand-alone statistics of a logically-[N, C, *] tensor (any strides handled via layout flag)."""
+    _require_cuda(x, "tracked tensor")
+    N, Cc = x.shape[0], x.shape[1]
+    hw = x.numel() // max(1, N * Cc)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    dt = dtype_code(x)
+    if x.dim() >= 3 and x.permute(0, *range(2, x.dim()), 1).is_contiguous():
+        call("vcd_chan_stats", _p(x), dt, _p(slot.raw), slot.near_zero, N, hw, Cc, 1, _st())
+    else:
+        x = x.contiguous()
+        call("vcd_chan_stats", _p(x), dt, _p(slot.raw), slot.near_zero, N, hw, Cc, 0, _st())
+    slot.finalize(N * hw)
+
+
+# ------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------
+class PackedWeights:
+    """bf16 GEMM operand packs of one conv / linear layer, refreshed when the parameters change."""
+
+    def __init__(self):
+        self.key = None
+        self.wf = self.wd = self.bias = None
+
+    def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+        key = (weight.data_ptr(), weight._version, weight.dtype, None if bias is None else (bias.data_ptr(), bias._version))
+        if key != self.key:
+            _require_cuda(weight, "conv weight")
+            w = weight.detach()
+            if not w.is_contiguous():
+                w = w.contiguous()
+            cout, cin = w.shape[0], w.shape[1]
+            kh, kw = (w.shape[2], w.shape[3]) if w.dim() == 4 else (1, 1)
+            self.wf = torch.empty(kh * kw * cout * cin, dtype=torch.bfloat16, device=w.device)
+            self.wd = torch.empty(kh * kw * cout * cin, dtype=torch.bfloat16, device=w.device)
+            self.bias = None if bias is None else torch.empty(cout, dtype=torch.float32, device=w.device)
+            call("vcd_pack_conv_weight", _p(w), _p(None if bias is None else bias.detach()), dtype_code(w), cout, cin,
+                 kh, kw, _p(self.wf), _p(self.wd), _p(self.bias), _st())
+            self.key = key
+        return self.wf, self.wd, self.bias
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, packs: PackedWeights, stride: int, pad_t: int, pad_l: int,
+                out_hw, impl: int):
+        x = _nhwc(x)
+        N, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        KH, KW = (weight.shape[2], weight.shape[3]) if weight.dim() == 4 else (1, 1)
+        Ho, Wo = out_hw
+        wf, wd, b32 = packs.get(weight, bias)
+        umma = impl != IMPL_SIMT and _lib.lib().vcd_conv_umma_supported(Cin, Cout, KH, KW, stride) == 1
+        planes = 0
+        xs = x
+        if stride == 2 and umma:
+            xs = torch.empty((N, 4, H // 2, W // 2, Cin), dtype=torch.bfloat16, device=x.device)
+            call("vcd_space_to_planes", _p(x), _p(xs), N, H, W, Cin, _st())
+            planes = 1
+        if residual is not None:
+            residual = _nhwc(residual)
+        y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+        call("vcd_conv2d_fprop", _p(xs), _p(wf), _p(b32), _p(residual), _p(y), N, H, W, Cin, Cout, KH, KW, stride,
+             pad_t, pad_l, Ho, Wo, planes, impl, _st())
+        ctx.save_for_backward(xs, weight, bias)
+        ctx.packs = packs
+        ctx.cfg = (N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl)
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, weight, bias = ctx.saved_tensors
+        N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl = ctx.cfg
+        dy = _nhwc(dy)
+        wf, wd, _ = ctx.packs.get(weight, bias)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if planes:
+                dxp = torch.empty((N, 4, H // 2, W // 2, Cin), dtype=torch.bfloat16, device=dy.device)
+                call("vcd_conv2d_dgrad", _p(dy), _p(wf), _p(wd), _p(dxp), N, H, W, Cin, Cout, KH, KW, stride, pad_t,
+                     pad_l, Ho, Wo, 1, impl, _st())
+                dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
+                call("vcd_planes_to_space", _p(dxp), _p(dx), N, H, W, Cin, _st())
+            else:
+                dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
+                call("vcd_conv2d_dgrad", _p(dy), _p(wf), _p(wd), _p(dx), N, H, W, Cin, Cout, KH, KW, stride, pad_t,
+                     pad_l, Ho, Wo, 0, impl, _st())
+        if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+            db = None if bias is None else torch.empty_like(bias)
+            nbytes = _lib.lib().vcd_conv2d_wgrad_ws_bytes(Cin, Cout, KH, KW)
+            ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
+            call("vcd_conv2d_wgrad", _p(xs), _p(dy), _p(dw), _p(db), dtype_code(weight), _p(ws), N, H, W, Cin, Cout,
+                 KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl, _st())
+        dres = dy if ctx.has_res and ctx.needs_input_grad[3] else None
+        return dx, dw, db, dres, None, None, None, None, None, None
+
+
+def conv2d(x, weight, bias, packs, stride=1, pad_t=1, pad_l=1, out_hw=None, residual=None, impl=None):
+    if out_hw is None:
+        out_hw = (x.shape[1], x.shape[2])
+    return _ConvFn.apply(x, weight, bias, residual, packs, stride, pad_t, pad_l, tuple(out_hw),
+                         _conv_impl if impl is None else impl)
+
+
+# ------------------------------------------------------------------------------------------
+# GroupNorm (+SiLU) with fused statistics
+# ------------------------------------------------------------------------------------------
+class _GroupNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups: int, eps: float, act: bool, slot_in: Optional[TrackSlot],
+                slot_out: Optional[TrackSlot]):
+        x = _nhwc(x)
+        N, C = x.shape[0], x.shape[-1]
+        hw = x.numel() // (N * C)
+        sums = torch.empty(N * groups * 2, dtype=torch.float64, device=x.device)
+        call("vcd_gn_stats", _p(x), _p(sums), _p(None if slot_in is None else slot_in.raw),
+             0.0 if slot_in is None else slot_in.near_zero, N, hw, C, groups, _st())
+        out = torch.empty_like(x)
+        g, b = gamma.detach(), beta.detach()
+        call("vcd_gn_apply_fwd", _p(x), _p(sums), _p(g), _p(b), dtype_code(g), _p(out),
+             _p(None if slot_out is None else slot_out.raw), 0.0 if slot_out is None else slot_out.near_zero,
+             float(eps), 1 if act else 0, N, hw, C, groups, _st())
+        if slot_in is not None:
+            slot_in.finalize(N * hw)
+        if slot_out is not None:
+            slot_out.finalize(N * hw)
+        ctx.save_for_backward(x, sums, gamma, beta)
+        ctx.cfg = (N, hw, C, groups, float(eps), 1 if act else 0)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, sums, gamma, beta = ctx.saved_tensors
+        N, hw, C, G, eps, act = ctx.cfg
+        dout = _nhwc(dout)
+        g, b = gamma.detach(), beta.detach()
+        pdt = dtype_code(g)
+        dsdb = torch.empty(N * C * 2, dtype=torch.float32, device=x.device)
+        call("vcd_gn_bwd_reduce", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), eps, act, N, hw, C, G, _st())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("vcd_gn_bwd_apply", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), _p(dx), eps, act, N, hw,
+                 C, G, _st())
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(beta)
+        call("vcd_gn_param_grad", _p(sums), _p(dsdb), _p(dgamma), _p(dbeta), pdt, eps, N, hw, C, G, _st())
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def group_norm(x, gamma, beta, groups, eps, act, slot_in=None, slot_out=None):
+    return _GroupNormFn.apply(x, gamma, beta, groups, eps, act, slot_in, slot_out)
+
+
+# ------------------------------------------------------------------------------------------
+# small element-wise ops
+# ------------------------------------------------------------------------------------------
+class _SiluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _nhwc(x)
+        y = torch.empty_like(x)
+        call("vcd_silu_fwd", _p(x), _p(y), x.numel(), _st())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _nhwc(dy)
+        dx = torch.empty_like(x)
+        call("vcd_silu_bwd", _p(x), _p(dy), _p(dx), x.numel(), _st())
+        return dx
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _nhwc(a), _nhwc(b)
+        o = torch.empty_like(a)
+        call("vcd_add", _p(a), _p(b), _p(o), a.numel(), _st())
+        return o
+
+    @staticmethod
+    def backward(ctx, d):
+        return d, d
+
+
+class _Upsample2xFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _nhwc(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
+        call("vcd_upsample2x_fwd", _p(x), _p(y), N, H, W, C, _st())
+        ctx.shape = (N, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C = ctx.shape
+        dy = _nhwc(dy)
+        dx = torch.empty((N, H, W, C), dtype=dy.dtype, device=dy.device)
+        call("vcd_upsample2x_bwd", _p(dy), _p(dx), N, H, W, C, _st())
+        return dx
+
+
+class _ToNHWC(torch.autograd.Function):
+    """[N, C, H, W] (fp32 | bf16, any strides) -> bf16 NHWC."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x, "model input")
+        N, C, H, W = x.shape
+        ctx.meta = (N, C, H, W, x.dtype)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        y = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device)
+        call("vcd_nchw_to_nhwc", _p(x), dtype_code(x), _p(y), N, C, H, W, _st())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W, dt = ctx.meta
+        dy = _nhwc(dy)
+        odt = dt if dt in (torch.float32, torch.bfloat16) else torch.float32
+        dx = torch.empty((N, C, H, W), dtype=odt, device=dy.device)
+        call("vcd_nhwc_to_nchw", _p(dy), _p(dx), dtype_code(dx), N, C, H, W, _st())
+        return dx.to(dt)
+
+
+class _ToNCHW(torch.autograd.Function):
+    """bf16 NHWC -> contiguous [N, C, H, W] in `dtype` (what train.py / evaluate.py consume)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        x = _nhwc(x)
+        N, H, W, C = x.shape
+        y = torch.empty((N, C, H, W), dtype=dtype, device=x.device)
+        call("vcd_nhwc_to_nchw", _p(x), _p(y), dtype_code(y), N, C, H, W, _st())
+        ctx.meta = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W = ctx.meta
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        dy = dy.contiguous()
+        dx = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dy.device)
+        call("vcd_nchw_to_nhwc", _p(dy), dtype_code(dy), _p(dx), N, C, H, W, _st())
+        return dx, None
+
+
+def silu(x):
+    return _SiluFn.apply(x)
+
+
+def add(a, b):
+    return _AddFn.apply(a, b)
+
+
+def upsample2x(x):
+    return _Upsample2xFn.apply(x)
+
+
+def to_nhwc(x):
+    """logical [N, C, H, W] -> physical bf16 [N, H, W, C] (zero-copy when already bf16 channels-last)."""
+    if x.dtype == torch.bfloat16 and x.permute(0, 2, 3, 1).is_contiguous():
+        return x.permute(0, 2, 3, 1)
+    return _ToNHWC.apply(x)
+
+
+def to_nchw(x, dtype=torch.float32):
+    return _ToNCHW.apply(x, dtype)
+
+
+# ------------------------------------------------------------------------------------------
+# attention core: softmax(Q K^T / sqrt(C)) V, one head (mid_block.attentions.0)
+# ------------------------------------------------------------------------------------------
+def _gemm_nt(A, B, D, batch, M, Nn, K, b_batched, alpha=1.0, bias=None, residual=None):
+    call("vcd_gemm_nt", _p(A), _p(B), _p(bias), _p(residual), _p(D), batch, M, Nn, K, 1 if b_batched else 0,
+         float(alpha), _st())
+
+
+def _gemm_tn(A, B, D, batch, M, Nn, K, reduce_batch):
+    nb = 1 if reduce_batch else batch
+    ws = torch.empty(nb * M * Nn, dtype=torch.float32, device=A.device)
+    call("vcd_gemm_tn", _p(A), _p(B), _p(D), dtype_code(D), _p(ws), batch, M, Nn, K, 1 if reduce_batch else 0, _st())
+
+
+def _transpose(x, batch, rows, cols):
+    y = torch.empty((batch, cols, rows), dtype=torch.bfloat16, device=x.device)
+    call("vcd_transpose_bf16", _p(x), _p(y), batch, rows, cols, _st())
+    return y
+
+
+class _AttnCoreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v):
+        q, k, v = _nhwc(q), _nhwc(k), _nhwc(v)
+        N, C = q.shape[0], q.shape[-1]
+        T = q.numel() // (N * C)
+        scale = 1.0 / math.sqrt(C)
+        dev = q.device
+        s = torch.empty((N, T, T), dtype=torch.bfloat16, device=dev)
+        _gemm_nt(q, k, s, N, T, T, C, True, alpha=scale)
+        p = torch.empty_like(s)
+        call("vcd_softmax_fwd", _p(s), _p(p), N * T, T, _st())
+        del s
+        vt = _transpose(v, N, T, C)  # [N][C][T]
+        o = torch.empty_like(q)
+        _gemm_nt(p, vt, o, N, T, C, T, True)
+        ctx.save_for_backward(q, k, v, p)
+        ctx.meta = (N, T, C, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, p = ctx.saved_tensors
+        N, T, C, scale = ctx.meta
+        do = _nhwc(do)
+        dev = q.device
+        dv = torch.empty_like(v)
+        _gemm_tn(p, do, dv, N, T, C, T, False)            # dV[j][c] = sum_i P[i][j] dO[i][c]
+        dp = torch.empty((N, T, T), dtype=torch.bfloat16, device=dev)
+        _gemm_nt(do, v, dp, N, T, T, C, True)              # dP[i][j] = sum_c dO[i][c] V[j][c]
+        ds = torch.empty_like(dp)
+        call("vcd_softmax_bwd", _p(p), _p(dp), _p(ds), scale, N * T, T, _st())
+        del dp
+        kt = _transpose(k, N, T, C)                        # [N][C][T]
+        dq = torch.empty_like(q)
+        _gemm_nt(ds, kt, dq, N, T, C, T, True)             # dQ[i][c] = sum_j dS[i][j] K[j][c]
+        dk = torch.empty_like(k)
+        _gemm_tn(ds, q, dk, N, T, C, T, False)             # dK[j][c] = sum_i dS[i][j] Q[i][c]
+        return dq, dk, dv
+
+
+def attention_core(q, k, v):
+    return _AttnCoreFn.apply(q, k, v)
+
+
+# ------------------------------------------------------------------------------------------
+# latent distribution and losses
+# ------------------------------------------------------------------------------------------
+class _GaussFn(torch.autograd.Function):
+    """moments [N,h,w,8] (+ noise [N,4,h,w] fp32) -> z [N,h,w,4] bf16, kl [N] fp32, mean/logvar [N,4,h,w] fp32."""
+
+    @staticmethod
+    def forward(ctx, moments, noise):
+        moments = _nhwc(moments)
+        N, h, w, C2 = moments.shape
+        L = C2 // 2
+        dev = moments.device
+        z = torch.empty((N, h, w, L), dtype=torch.bfloat16, device=dev)
+        kl = torch.empty(N, dtype=torch.float32, device=dev)
+        mean = torch.empty((N, L, h, w), dtype=torch.float32, device=dev)
+        logvar = torch.empty((N, L, h, w), dtype=torch.float32, device=dev)
+        if noise is not None:
+            noise = noise.to(torch.float32).contiguous()
+        call("vcd_gauss_sample_kl_fwd", _p(moments), _p(noise), _p(z), _p(mean), _p(logvar), _p(kl), N, h * w, L, _st())
+        ctx.save_for_backward(moments, noise)
+        ctx.meta = (N, h * w, L)
+        ctx.mark_non_differentiable(mean, logvar)
+        return z, kl, mean, logvar
+
+    @staticmethod
+    def backward(ctx, dz, dkl, _dm, _dl):
+        moments, noise = ctx.saved_tensors
+        N, hw, L = ctx.meta
+        if dz is not None:
+            dz = _nhwc(dz)
+        if dkl is not None:
+            dkl = dkl.to(torch.float32).contiguous()
+        dm = torch.empty_like(moments)
+        call("vcd_gauss_sample_kl_bwd", _p(moments), _p(noise), _p(dz), _p(dkl), _p(dm), N, hw, L, _st())
+        return dm, None
+
+
+def gauss_sample_kl(moments, noise):
+    return _GaussFn.apply(moments, noise)
+
+
+class _MseFn(torch.autograd.Function):
+    """mean((rec - x)^2) with rec bf16 NHWC and x the fp32 NCHW loader tensor (train.py:289)."""
+
+    @staticmethod
+    def forward(ctx, rec, x):
+        rec = _nhwc(rec)
+        N, H, W, C = rec.shape
+        x = x.to(torch.float32).contiguous()
+        loss = torch.empty(1, dtype=torch.float64, device=rec.device)
+        drec = torch.empty_like(rec)
+        numel = rec.numel()
+        call("vcd_mse_fwd_bwd", _p(rec), _p(x), _p(loss), _p(drec), 1.0 / numel, N, C, H, W, _st())
+        ctx.save_for_backward(drec)
+        return (loss / numel).to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (drec,) = ctx.saved_tensors
+        return drec * g.to(drec.dtype), None
+
+
+def mse_loss(rec_nhwc, x_nchw):
+    return _MseFn.apply(rec_nhwc, x_nchw)
