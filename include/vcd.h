@@ -31,8 +31,10 @@ typedef void* vcd_stream_t; /* cudaStream_t */
 #define VCD_F32 0
 #define VCD_BF16 1
 
-/* conv implementation selector */
-#define VCD_IMPL_AUTO 0 /* tcgen05 implicit GEMM when the shape allows, else SIMT direct */
+/* conv implementation selector.  AUTO: tcgen05 implicit GEMM for 128-multiple channels; small-channel layers
+ * (3->128, 128->3, 4->512, 512->8) also run on the tcgen05 kernel, as a narrow-N implicit GEMM or an im2col
+ * patch + GEMM with a caller-provided workspace (vcd_conv2d_*_ws_bytes); SIMT only for the 1x1 quant convs */
+#define VCD_IMPL_AUTO 0
 #define VCD_IMPL_SIMT 1 /* CUDA-core direct convolution (small-channel layers, cross-check) */
 #define VCD_IMPL_UMMA 2 /* tcgen05/TMEM/TMA implicit GEMM; error if the shape is unsupported */
 
@@ -57,17 +59,20 @@ int vcd_pack_conv_weight(const void* w, const void* bias, int dtype, int Cout, i
  * Downsample2D's asymmetric (0,1,0,1) pad is pad_t = pad_l = 0 with Ho = H/2 (zero fill
  * past the bottom/right edge).  x_planes != 0 (stride 2 only) means x is the parity-plane
  * layout [N][2][2][H/2][W/2][C] written by vcd_space_to_planes. */
-int vcd_conv2d_fprop(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y,
+int64_t vcd_conv2d_fprop_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
+int vcd_conv2d_fprop(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y, void* ws,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
                      int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream);
 /* dx = conv_transpose(dy).  dx_planes != 0 (stride 2 only): dx is written in parity-plane layout. */
-int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void* w_dgrad, void* dx,
+int64_t vcd_conv2d_dgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
+int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void* w_dgrad, void* dx, void* ws,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
                      int Ho, int Wo, int dx_planes, int impl, vcd_stream_t stream);
-/* dw (OIHW, `dtype`) and db ([Cout], `dtype`, may be NULL).  ws: fp32 workspace of
- * vcd_conv2d_wgrad_ws_bytes() bytes (zeroed by the call). */
-int64_t vcd_conv2d_wgrad_ws_bytes(int Cin, int Cout, int KH, int KW);
-int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, int dtype, void* ws,
+/* dw (OIHW, `dtype`) and db ([Cout], `dtype`, may be NULL).  ws: workspace of vcd_conv2d_wgrad_ws_bytes()
+ * bytes (zeroed by the call).  db_colsum (fp32 [Cout], may be NULL): column sums of dy already produced by
+ * the kernel that wrote dy (vcd_gn_bwd_apply), which saves the bias-gradient pass over dy. */
+int64_t vcd_conv2d_wgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
+int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, const float* db_colsum, int dtype, void* ws,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
                      int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream);
 
@@ -100,9 +105,12 @@ int vcd_gn_apply_fwd(const void* x, const double* sums, const void* gamma, const
 int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
                       int param_dtype, float* dsdb, float eps, int act_silu,
                       int N, int HW, int C, int G, vcd_stream_t stream);
+/* dx = GroupNorm/SiLU backward (+ dres, the gradient arriving over the block's skip connection, may be NULL);
+ * dx_colsum (fp32 [C], may be NULL) receives the per-channel sums of dx = the bias gradient of the conv that
+ * produced x */
 int vcd_gn_bwd_apply(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
-                     int param_dtype, const float* dsdb, void* dx, float eps, int act_silu,
-                     int N, int HW, int C, int G, vcd_stream_t stream);
+                     int param_dtype, const float* dsdb, void* dx, const void* dres, float* dx_colsum,
+                     float eps, int act_silu, int N, int HW, int C, int G, vcd_stream_t stream);
 int vcd_gn_param_grad(const double* sums, const float* dsdb, void* dgamma, void* dbeta, int param_dtype,
                       float eps, int N, int HW, int C, int G, vcd_stream_t stream);
 /* stand-alone SiLU (only used when a foreign forward hook needs the pre-activation tensor) */

@@ -147,7 +147,9 @@ def test_tracked_training_step_with_classify_and_nudge(vcd, pair):
     hooks = [
         oracle.encoder.conv_in.register_forward_hook(lambda m, i, o: ref["conv_in"].append(oc.mean_abs_per_channel(o))),
         oracle.get_submodule(gn_names[0]).register_forward_hook(
-            lambda m, i, o: (ref["gn0_out"].append(oc.mean_abs_per_channel(o)), ref["gn0_in"].append(oc.mean_abs_per_channel(i[0])))),
+            lambda m, i, o: ref["gn0_out"].append(oc.mean_abs_per_channel(o))),
+        oracle.get_submodule(gn_names[0]).register_forward_pre_hook(
+            lambda m, i: ref["gn0_in"].append(oc.mean_abs_per_channel(i[0]))),
         oracle.get_submodule(gn_names[1]).register_forward_hook(lambda m, i, o: ref["gn1_out"].append(oc.mean_abs_per_channel(o))),
     ]
     torch.manual_seed(3)

@@ -19,10 +19,12 @@ SIGNATURES = {
     "vcd_version": (_i, []),
     "vcd_conv_umma_supported": (_i, [_i] * 5),
     "vcd_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
-    "vcd_conv2d_fprop": (_i, [_p] * 5 + [_i] * 14 + [_p]),
-    "vcd_conv2d_dgrad": (_i, [_p] * 4 + [_i] * 14 + [_p]),
-    "vcd_conv2d_wgrad_ws_bytes": (_i64, [_i] * 4),
-    "vcd_conv2d_wgrad": (_i, [_p] * 4 + [_i] + [_p] + [_i] * 14 + [_p]),
+    "vcd_conv2d_fprop_ws_bytes": (_i64, [_i] * 8),
+    "vcd_conv2d_fprop": (_i, [_p] * 6 + [_i] * 14 + [_p]),
+    "vcd_conv2d_dgrad_ws_bytes": (_i64, [_i] * 8),
+    "vcd_conv2d_dgrad": (_i, [_p] * 5 + [_i] * 14 + [_p]),
+    "vcd_conv2d_wgrad_ws_bytes": (_i64, [_i] * 8),
+    "vcd_conv2d_wgrad": (_i, [_p] * 5 + [_i] + [_p] + [_i] * 14 + [_p]),
     "vcd_space_to_planes": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vcd_planes_to_space": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vcd_upsample2x_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
@@ -33,7 +35,7 @@ SIGNATURES = {
     "vcd_gn_stats": (_i, [_p, _p, _p, _f, _i, _i, _i, _i, _p]),
     "vcd_gn_apply_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _f, _f, _i, _i, _i, _i, _i, _p]),
     "vcd_gn_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _i, _i, _i, _i, _i, _p]),
-    "vcd_gn_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p]),
+    "vcd_gn_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p]),
     "vcd_gn_param_grad": (_i, [_p, _p, _p, _p, _i, _f, _i, _i, _i, _i, _p]),
     "vcd_silu_fwd": (_i, [_p, _p, _i64, _p]),
     "vcd_silu_bwd": (_i, [_p, _p, _p, _i64, _p]),

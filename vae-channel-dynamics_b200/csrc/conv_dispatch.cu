@@ -222,75 +222,61 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
   return umma_launch(mA, mB, p, bn, st);
 }
 
-__global__ void convert_f32_kernel(const float* __restrict__ in, void* __restrict__ out, int dt, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    store_param(out, dt, i, in[i]);
-}
 
-}  // namespace
-
-extern "C" int vcd_conv_umma_supported(int Cin, int Cout, int KH, int KW, int stride) {
-  return umma_shape_ok(Cin, Cout, KH, KW, stride) ? 1 : 0;
-}
-
-extern "C" int vcd_conv2d_fprop(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y,
-                                int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
-                                int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream) {
-  VCD_CHECK_ARG(x && w_fprop && y, "conv fprop: null pointer");
-  bool ok = umma_shape_ok(Cin, Cout, KH, KW, stride);
-  if (impl == VCD_IMPL_UMMA) VCD_CHECK_ARG(ok, "conv fprop: shape (Cin=%d,Cout=%d,k=%d,s=%d) not supported by the tcgen05 path", Cin, Cout, KH, stride);
-  if (ok && impl != VCD_IMPL_SIMT)
-    return umma_fprop(x, w_fprop, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, x_planes,
-                      as_stream(stream));
-  VCD_CHECK_ARG(!x_planes, "conv fprop (SIMT): parity-plane input not supported");
-  return simt_conv_fprop(x, w_fprop, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo,
-                         as_stream(stream));
-}
-
-extern "C" int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void* w_dgrad, void* dx, int N, int H, int W,
-                                int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo,
-                                int dx_planes, int impl, vcd_stream_t stream) {
-  (void)w_fprop;
-  VCD_CHECK_ARG(dy && dx, "conv dgrad: null pointer");
-  bool ok = umma_shape_ok(Cin, Cout, KH, KW, stride);
-  if (impl == VCD_IMPL_UMMA) VCD_CHECK_ARG(ok, "conv dgrad: shape not supported by the tcgen05 path");
-  if (ok && impl != VCD_IMPL_SIMT)
-    return umma_dgrad(dy, w_dgrad, dx, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, dx_planes,
-                      as_stream(stream));
-  VCD_CHECK_ARG(!dx_planes, "conv dgrad (SIMT): parity-plane output not supported");
-  return simt_conv_dgrad(dy, w_dgrad, dx, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, as_stream(stream));
-}
-
-extern "C" int64_t vcd_conv2d_wgrad_ws_bytes(int Cin, int Cout, int KH, int KW) {
-  return ((int64_t)KH * KW * Cout * Cin + Cout) * (int64_t)sizeof(float);
-}
-
-extern "C" int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, int dtype, void* ws, int N, int H,
-                                int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo,
-                                int x_planes, int impl, vcd_stream_t stream) {
-  VCD_CHECK_ARG(x && dy && dw && ws, "conv wgrad: null pointer");
-  cudaStream_t st = as_stream(stream);
-  VCD_CUDA(cudaMemsetAsync(ws, 0, (size_t)vcd_conv2d_wgrad_ws_bytes(Cin, Cout, KH, KW), st));
-  float* wsf = (float*)ws;
-  bool ok = umma_shape_ok(Cin, Cout, KH, KW, stride);
-  if (impl == VCD_IMPL_UMMA) VCD_CHECK_ARG(ok, "conv wgrad: shape not supported by the tcgen05 path");
-  int rc;
-  if (ok && impl != VCD_IMPL_SIMT) {
-    rc = umma_wgrad(x, dy, wsf, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, x_planes, st);
-  } else {
-    VCD_CHECK_ARG(!x_planes, "conv wgrad (SIMT): parity-plane input not supported");
-    rc = simt_conv_wgrad(x, dy, wsf, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, st);
+// ---------------------------------------------------------------- small-channel layers on the GEMM kernel
+// patch[px][col], col = t*S + s  ->  src[n, h + dh[t], w + dw[t], s]   (zero outside the image / beyond taps*S)
+struct PatchTaps { int n; int dh[9], dw[9]; };
+__global__ void __launch_bounds__(256) im2col_small_kernel(const bf16* __restrict__ src, bf16* __restrict__ patch, int N,
+                                                           int H, int W, int S, int Kp, PatchTaps taps) {
+  const int V = Kp / 8;
+  const int64_t total = (int64_t)N * H * W * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    const int64_t px = i / V;
+    const int w = (int)(px % W);
+    const int64_t r = px / W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = v * 8 + j;
+      const int t = col / S, c = col - t * S;
+      float val = 0.f;
+      if (t < taps.n) {
+        const int hi = h + taps.dh[t], wi = w + taps.dw[t];
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = __bfloat162float(src[(((int64_t)n * H + hi) * W + wi) * S + c]);
+      }
+      f[j] = val;
+    }
+    st8(patch + px * Kp + v * 8, pack8(f));
   }
-  if (rc) return rc;
-  if (db && (rc = conv_bias_grad(dy, wsf + (int64_t)KH * KW * Cout * Cin, (int64_t)N * Ho * Wo, Cout, st))) return rc;
-  return conv_wgrad_finalize(wsf, dw, db, dtype, Cout, Cin, KH * KW, st);
 }
+// wk[o][t*S + s] = pack[t][o][s]   (pack = w_fprop [tap][Cout][Cin] or w_dgrad [tap][Cin][Cout])
+__global__ void repack_small_kernel(const bf16* __restrict__ pack, bf16* __restrict__ wk, int taps, int O, int S, int Kp) {
+  const int total = O * Kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int col = i % Kp, o = i / Kp;
+    const int t = col / S, c = col - t * S;
+    wk[i] = t < taps ? pack[((int64_t)t * O + o) * S + c] : __float2bfloat16_rn(0.f);
+  }
+}
+// D [big][Np] (col = t*S + s) -> ws [tap][Cout][Cin]; big_is_cout: big = co, s = ci; else big = ci, s = co
+__global__ void wgrad_small_reorder_kernel(const float* __restrict__ D, float* __restrict__ ws, int taps, int Cout, int Cin,
+                                           int Np, int big_is_cout) {
+  const int total = taps * Cout * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % Cin;
+    const int r = i / Cin;
+    const int co = r % Cout, t = r / Cout;
+    ws[i] = big_is_cout ? D[(int64_t)co * Np + t * Cin + ci] : D[(int64_t)ci * Np + t * Cout + co];
+  }
+}
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
-// D[b][m][n] = alpha * sum_k A[b][m][k] B[(b)][n][k] (+bias[n]) (+residual[b][m][n])
-extern "C" int vcd_gemm_nt(const void* A, const void* B, const float* bias, const void* residual, void* D, int batch,
-                           int M, int Nn, int K, int b_batched, float alpha, vcd_stream_t stream) {
-  VCD_CHECK_ARG(A && B && D, "gemm_nt: null pointer");
-  VCD_CHECK_ARG(K % 64 == 0 && Nn % 8 == 0, "gemm_nt: need K %% 64 == 0 and N %% 8 == 0 (K=%d N=%d)", K, Nn);
+int gemm_nt_impl(const void* A, const void* B, const float* bias, const void* residual, void* D, int batch, int M, int Nn,
+                 int K, int b_batched, float alpha, cudaStream_t st) {
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.form = 0;
@@ -311,27 +297,24 @@ extern "C" int vcd_gemm_nt(const void* A, const void* B, const float* bias, cons
   int rc;
   if ((rc = make_act_map(&mA, A, K, M, 1, 1, batch, 64, 128, 1, 1))) return rc;
   if ((rc = make_act_map(&mB, B, K, b_batched ? batch * Nn : Nn, 1, 1, 1, 64, bn, 1, 1))) return rc;
-  return umma_launch(mA, mB, p, bn, as_stream(stream));
+  return umma_launch(mA, mB, p, bn, st);
 }
 
-// D[b][m][n] = sum_k A[b][k][m] B[b][k][n]; reduce_batch sums over b as well (Linear wgrad)
-extern "C" int vcd_gemm_tn(const void* A, const void* B, void* D, int d_dtype, void* ws_f32, int batch, int M, int Nn,
-                           int K, int reduce_batch, vcd_stream_t stream) {
-  VCD_CHECK_ARG(A && B && D && ws_f32, "gemm_tn: null pointer");
-  VCD_CHECK_ARG(M % 8 == 0 && Nn % 8 == 0, "gemm_tn: need M %% 8 == 0 and N %% 8 == 0");
-  cudaStream_t st = as_stream(stream);
+// acc (fp32 [batches][M][Nn]) = sum_k A[b][k][m] B[b][k][n]; acc is zeroed here
+int gemm_tn_impl(const void* A, const void* B, float* acc, int batch, int M, int Nn, int64_t K, int reduce_batch,
+                 cudaStream_t st) {
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.form = 1;
-  p.W = K; p.H = 1; p.Nimg = batch;
+  p.W = (int)K; p.H = 1; p.Nimg = batch;
   p.tile_w = 64; p.tile_h = 1; p.tile_n = 1;
-  p.tiles_w = (K + 63) / 64; p.tiles_h = 1; p.tiles_n = batch;
+  p.tiles_w = (int)((K + 63) / 64); p.tiles_h = 1; p.tiles_n = batch;
   p.ntaps = 1;
   const int bn = pick_block_n(Nn);
   p.n_tiles = (Nn + bn - 1) / bn;
   p.m_tiles = (M + 127) / 128;
   p.Mout = M; p.Nout = Nn;
-  p.acc = (float*)ws_f32;
+  p.acc = acc;
   p.batches = reduce_batch ? 1 : batch;
   p.k_tiles = reduce_batch ? p.tiles_w * batch : p.tiles_w;
   const int base_tiles = p.batches * p.m_tiles * p.n_tiles;
@@ -342,13 +325,231 @@ extern "C" int vcd_gemm_tn(const void* A, const void* B, void* D, int d_dtype, v
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
   set_form1_desc(p, bn);
   p.total_tiles = base_tiles * p.splits;
-  const int64_t out_elems = (int64_t)p.batches * M * Nn;
-  VCD_CUDA(cudaMemsetAsync(ws_f32, 0, out_elems * sizeof(float), st));
+  VCD_CUDA(cudaMemsetAsync(acc, 0, (size_t)p.batches * M * Nn * sizeof(float), st));
   CUtensorMap mA, mB;
   int rc;
-  if ((rc = make_act_map(&mA, A, M, K, 1, 1, batch, 64, 64, 1, 1))) return rc;
-  if ((rc = make_act_map(&mB, B, Nn, K, 1, 1, batch, 64, 64, 1, 1))) return rc;
-  if ((rc = umma_launch(mA, mB, p, bn, st))) return rc;
+  if ((rc = make_act_map(&mA, A, M, (int)K, 1, 1, batch, 64, 64, 1, 1))) return rc;
+  if ((rc = make_act_map(&mB, B, Nn, (int)K, 1, 1, batch, 64, 64, 1, 1))) return rc;
+  return umma_launch(mA, mB, p, bn, st);
+}
+
+// small-channel classification (stride 1 only)
+bool narrow_out_ok(int Kc, int Nout, int stride) { return stride == 1 && Kc % 64 == 0 && Nout < 128 && Nout >= 1; }
+bool patch_ok(int small, int big, int stride, int taps) { return stride == 1 && small <= 8 && big >= 32 && big % 8 == 0 && taps <= 9; }
+
+PatchTaps patch_taps(int KH, int KW, int pad_t, int pad_l, int sign) {
+  PatchTaps t;
+  t.n = KH * KW;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      t.dh[kh * KW + kw] = sign * (kh - pad_t);
+      t.dw[kh * KW + kw] = sign * (kw - pad_l);
+    }
+  return t;
+}
+int ew_blocks(int64_t work) {
+  int64_t b = (work + 255) / 256, cap = (int64_t)vcd_num_sms() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// out[px][O] = bias + sum_{t,s} src[px + shift_t][s] * pack[t][O][s]  via  im2col patch + GEMM (K = taps*S padded to 64)
+int patch_gemm(const void* src, const void* pack, const float* bias, void* out, void* ws, int N, int H, int W, int S, int O,
+               int KH, int KW, int pad_t, int pad_l, int sign, cudaStream_t st) {
+  VCD_CHECK_ARG(ws != nullptr, "small-channel conv needs a workspace (vcd_conv2d_*_ws_bytes)");
+  const int taps = KH * KW, Kp = round_up(taps * S, 64);
+  const int64_t px = (int64_t)N * H * W;
+  bf16* patch = (bf16*)ws;
+  bf16* wk = (bf16*)((char*)ws + align256(px * Kp * 2));
+  im2col_small_kernel<<<ew_blocks(px * (Kp / 8)), 256, 0, st>>>((const bf16*)src, patch, N, H, W, S, Kp,
+                                                                patch_taps(KH, KW, pad_t, pad_l, sign));
+  VCD_LAUNCH_CHECK();
+  repack_small_kernel<<<ew_blocks((int64_t)O * Kp), 256, 0, st>>>((const bf16*)pack, wk, taps, O, S, Kp);
+  VCD_LAUNCH_CHECK();
+  VCD_CHECK_ARG(px < (1ll << 31), "small-channel conv: too many pixels");
+  return gemm_nt_impl(patch, wk, bias, nullptr, out, 1, (int)px, O, Kp, 0, 1.f, st);
+}
+int64_t patch_gemm_ws(int64_t px, int S, int O, int taps) {
+  const int Kp = round_up(taps * S, 64);
+  return align256(px * Kp * 2) + align256((int64_t)O * Kp * 2);
+}
+
+// narrow-N implicit GEMM: fprop with Cout < 128 (or dgrad with Cin < 128); weights pack [tap][Nout][Kc] used as is
+int narrow_conv(const void* in, const void* pack, const float* bias, void* out, int N, int H, int W, int Kc, int Nout,
+                int KH, int KW, int pad_t, int pad_l, int sign, cudaStream_t st) {
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.form = 0;
+  choose_tile(128, W, H, N, p);
+  p.ntaps = KH * KW;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      int t = kh * KW + kw;
+      p.tap_dh[t] = sign * (kh - pad_t); p.tap_dw[t] = sign * (kw - pad_l); p.tap_plane[t] = 0;
+      p.tap_brow[t] = t * Nout;
+    }
+  p.n_tiles = 1; p.kc_per_tap = Kc / 64;
+  p.out = (bf16*)out; p.bias = bias; p.alpha = 1.f;
+  p.out_sn = (long long)H * W * Nout; p.out_sh = (long long)W * Nout; p.out_sw = Nout;
+  p.Nout = Nout;
+  set_form0_desc(p, 128);
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  CUtensorMap mA, mB;
+  int rc;
+  if ((rc = make_act_map(&mA, in, Kc, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+  if ((rc = make_act_map(&mB, pack, Kc, KH * KW * Nout, 1, 1, 1, 64, 128, 1, 1))) return rc;
+  return umma_launch(mA, mB, p, 128, st);
+}
+
+__global__ void convert_f32_kernel(const float* __restrict__ in, void* __restrict__ out, int dt, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    store_param(out, dt, i, in[i]);
+}
+
+}  // namespace
+
+extern "C" int vcd_conv_umma_supported(int Cin, int Cout, int KH, int KW, int stride) {
+  return umma_shape_ok(Cin, Cout, KH, KW, stride) ? 1 : 0;
+}
+
+// ---- which path serves a layer (AUTO): 2 = tcgen05 implicit GEMM, 3 = narrow-N implicit GEMM,
+//      4 = im2col patch + GEMM, 1 = SIMT
+static int fprop_path(int Cin, int Cout, int KH, int KW, int stride) {
+  if (umma_shape_ok(Cin, Cout, KH, KW, stride)) return 2;
+  if (narrow_out_ok(Cin, Cout, stride) && KH * KW <= 9) return 3;
+  if (patch_ok(Cin, Cout, stride, KH * KW)) return 4;
+  return 1;
+}
+static int dgrad_path(int Cin, int Cout, int KH, int KW, int stride) {
+  if (umma_shape_ok(Cin, Cout, KH, KW, stride)) return 2;
+  if (narrow_out_ok(Cout, Cin, stride) && KH * KW <= 9) return 3;
+  if (patch_ok(Cout, Cin, stride, KH * KW)) return 4;
+  return 1;
+}
+static int wgrad_path(int Cin, int Cout, int KH, int KW, int stride) {
+  if (umma_shape_ok(Cin, Cout, KH, KW, stride)) return 2;
+  if (patch_ok(Cin, Cout, stride, KH * KW) || patch_ok(Cout, Cin, stride, KH * KW)) return 4;
+  return 1;
+}
+
+extern "C" int64_t vcd_conv2d_fprop_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
+  return fprop_path(Cin, Cout, KH, KW, stride) == 4 ? patch_gemm_ws((int64_t)N * H * W, Cin, Cout, KH * KW) : 0;
+}
+extern "C" int64_t vcd_conv2d_dgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
+  return dgrad_path(Cin, Cout, KH, KW, stride) == 4 ? patch_gemm_ws((int64_t)N * H * W, Cout, Cin, KH * KW) : 0;
+}
+
+extern "C" int vcd_conv2d_fprop(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y,
+                                void* ws, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t,
+                                int pad_l, int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream) {
+  VCD_CHECK_ARG(x && w_fprop && y, "conv fprop: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int path = impl == VCD_IMPL_SIMT ? 1 : fprop_path(Cin, Cout, KH, KW, stride);
+  if (impl == VCD_IMPL_UMMA)
+    VCD_CHECK_ARG(path != 1, "conv fprop: shape (Cin=%d,Cout=%d,k=%d,s=%d) has no tcgen05 path", Cin, Cout, KH, stride);
+  if (path == 2)
+    return umma_fprop(x, w_fprop, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, x_planes, st);
+  VCD_CHECK_ARG(!x_planes, "conv fprop: parity-plane input only on the tcgen05 stride-2 path");
+  if (path == 3 && !residual)
+    return narrow_conv(x, w_fprop, bias, y, N, H, W, Cin, Cout, KH, KW, pad_t, pad_l, +1, st);
+  if (path == 4 && !residual)
+    return patch_gemm(x, w_fprop, bias, y, ws, N, H, W, Cin, Cout, KH, KW, pad_t, pad_l, +1, st);
+  return simt_conv_fprop(x, w_fprop, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, st);
+}
+
+extern "C" int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void* w_dgrad, void* dx, void* ws, int N,
+                                int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int Ho,
+                                int Wo, int dx_planes, int impl, vcd_stream_t stream) {
+  (void)w_fprop;
+  VCD_CHECK_ARG(dy && dx, "conv dgrad: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int path = impl == VCD_IMPL_SIMT ? 1 : dgrad_path(Cin, Cout, KH, KW, stride);
+  if (impl == VCD_IMPL_UMMA) VCD_CHECK_ARG(path != 1, "conv dgrad: shape has no tcgen05 path");
+  if (path == 2)
+    return umma_dgrad(dy, w_dgrad, dx, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, dx_planes, st);
+  VCD_CHECK_ARG(!dx_planes, "conv dgrad: parity-plane output only on the tcgen05 stride-2 path");
+  VCD_CHECK_ARG(w_dgrad != nullptr, "conv dgrad needs the w_dgrad pack");
+  // dx[q][ci] = sum_t sum_co dy[q - (k - pad)][co] * w_dgrad[t][ci][co]
+  if (path == 3) return narrow_conv(dy, w_dgrad, nullptr, dx, N, H, W, Cout, Cin, KH, KW, pad_t, pad_l, -1, st);
+  if (path == 4) return patch_gemm(dy, w_dgrad, nullptr, dx, ws, N, H, W, Cout, Cin, KH, KW, pad_t, pad_l, -1, st);
+  return simt_conv_dgrad(dy, w_dgrad, dx, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, st);
+}
+
+// workspace: fp32 [tap][Cout][Cin] + [Cout]  (+ small-channel path: bf16 patch [px][Np] + fp32 D [big][Np])
+extern "C" int64_t vcd_conv2d_wgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
+  int64_t base = align256(((int64_t)KH * KW * Cout * Cin + Cout) * (int64_t)sizeof(float));
+  if (wgrad_path(Cin, Cout, KH, KW, stride) == 4) {
+    const int small = Cin <= 8 ? Cin : Cout, big = Cin <= 8 ? Cout : Cin;
+    const int Np = round_up(KH * KW * small, 8);
+    base += align256((int64_t)N * H * W * Np * 2) + align256((int64_t)big * Np * 4);
+  }
+  return base;
+}
+
+extern "C" int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, const float* db_colsum, int dtype,
+                                void* ws, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t,
+                                int pad_l, int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream) {
+  VCD_CHECK_ARG(x && dy && dw && ws, "conv wgrad: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int taps = KH * KW;
+  const int64_t main_elems = (int64_t)taps * Cout * Cin;
+  VCD_CUDA(cudaMemsetAsync(ws, 0, (size_t)(main_elems + Cout) * sizeof(float), st));
+  float* wsf = (float*)ws;
+  const int path = impl == VCD_IMPL_SIMT ? 1 : wgrad_path(Cin, Cout, KH, KW, stride);
+  if (impl == VCD_IMPL_UMMA) VCD_CHECK_ARG(path != 1, "conv wgrad: shape has no tcgen05 path");
+  int rc;
+  if (path == 2) {
+    rc = umma_wgrad(x, dy, wsf, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, x_planes, st);
+  } else if (path == 4) {
+    VCD_CHECK_ARG(!x_planes, "conv wgrad: parity-plane input only on the tcgen05 stride-2 path");
+    const bool small_in = Cin <= 8 && patch_ok(Cin, Cout, stride, taps);
+    const int small = small_in ? Cin : Cout, big = small_in ? Cout : Cin;
+    const int Np = round_up(taps * small, 8);
+    const int64_t px = (int64_t)N * H * W;
+    VCD_CHECK_ARG(px < (1ll << 31), "conv wgrad: too many pixels");
+    char* base = (char*)ws + align256((main_elems + Cout) * (int64_t)sizeof(float));
+    bf16* patch = (bf16*)base;
+    float* D = (float*)(base + align256(px * Np * 2));
+    // small_in : patch = im2col(x, +shift), big tensor = dy   -> D[co][t*Cin+ci]
+    // small_out: patch = im2col(dy, -shift), big tensor = x   -> D[ci][t*Cout+co]
+    im2col_small_kernel<<<ew_blocks(px * (Np / 8)), 256, 0, st>>>((const bf16*)(small_in ? x : dy), patch, N, H, W, small,
+                                                                  Np, patch_taps(KH, KW, pad_t, pad_l, small_in ? +1 : -1));
+    VCD_LAUNCH_CHECK();
+    if ((rc = gemm_tn_impl(small_in ? dy : x, patch, D, 1, big, Np, px, 1, st))) return rc;
+    wgrad_small_reorder_kernel<<<ew_blocks(main_elems), 256, 0, st>>>(D, wsf, taps, Cout, Cin, Np, small_in ? 1 : 0);
+    VCD_LAUNCH_CHECK();
+    rc = 0;
+  } else {
+    VCD_CHECK_ARG(!x_planes, "conv wgrad (SIMT): parity-plane input not supported");
+    rc = simt_conv_wgrad(x, dy, wsf, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, st);
+  }
+  if (rc) return rc;
+  if (db) {
+    if (db_colsum) {
+      VCD_CUDA(cudaMemcpyAsync(wsf + main_elems, db_colsum, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if ((rc = conv_bias_grad(dy, wsf + main_elems, (int64_t)N * Ho * Wo, Cout, st))) {
+      return rc;
+    }
+  }
+  return conv_wgrad_finalize(wsf, dw, db, dtype, Cout, Cin, taps, st);
+}
+
+// D[b][m][n] = alpha * sum_k A[b][m][k] B[(b)][n][k] (+bias[n]) (+residual[b][m][n])
+extern "C" int vcd_gemm_nt(const void* A, const void* B, const float* bias, const void* residual, void* D, int batch,
+                           int M, int Nn, int K, int b_batched, float alpha, vcd_stream_t stream) {
+  VCD_CHECK_ARG(A && B && D, "gemm_nt: null pointer");
+  VCD_CHECK_ARG(K % 64 == 0 && Nn % 8 == 0, "gemm_nt: need K %% 64 == 0 and N %% 8 == 0 (K=%d N=%d)", K, Nn);
+  return gemm_nt_impl(A, B, bias, residual, D, batch, M, Nn, K, b_batched, alpha, as_stream(stream));
+}
+
+// D[b][m][n] = sum_k A[b][k][m] B[b][k][n]; reduce_batch sums over b as well (Linear wgrad)
+extern "C" int vcd_gemm_tn(const void* A, const void* B, void* D, int d_dtype, void* ws_f32, int batch, int M, int Nn,
+                           int K, int reduce_batch, vcd_stream_t stream) {
+  VCD_CHECK_ARG(A && B && D && ws_f32, "gemm_tn: null pointer");
+  VCD_CHECK_ARG(M % 8 == 0 && Nn % 8 == 0, "gemm_tn: need M %% 8 == 0 and N %% 8 == 0");
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if ((rc = gemm_tn_impl(A, B, (float*)ws_f32, batch, M, Nn, K, reduce_batch, st))) return rc;
+  const int64_t out_elems = (int64_t)(reduce_batch ? 1 : batch) * M * Nn;
   int64_t blocks = ceil_div64(out_elems, 256);
   if (blocks > vcd_num_sms() * 8) blocks = vcd_num_sms() * 8;
   convert_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)ws_f32, D, d_dtype, out_elems);

@@ -15,6 +15,8 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kIters = 32;  // pixels per thread per block
 
+constexpr int kUnroll = 4;
+
 struct Map {
   int V, PL, v, pl, c0;
   int64_t p_begin, p_end;
@@ -56,18 +58,28 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restri
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0.f;
   const bf16* xb = x + (int64_t)n * HW * C + m.c0;
-  for (int64_t p = m.p_begin + m.pl; p < m.p_end; p += m.PL) {
-    float f[8];
-    unpack8(ld8(xb + p * C), f);
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
+    bf16x8 v[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j] += f[j];
-      q[j] += f[j] * f[j];
-      if (STATS) {
-        float a = fabsf(f[j]);
-        sa[j] += a;
-        mx[j] = fmaxf(mx[j], a);
-        nz[j] += (a < near_zero) ? 1.f : 0.f;
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p < m.p_end) v[u] = ld8(xb + p * C);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (p0 + (int64_t)u * m.PL >= m.p_end) break;
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] += f[j] * f[j];
+        if (STATS) {
+          float a = fabsf(f[j]);
+          sa[j] += a;
+          mx[j] = fmaxf(mx[j], a);
+          nz[j] += (a < near_zero) ? 1.f : 0.f;
+        }
       }
     }
   }
@@ -131,23 +143,34 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const bf16* __restri
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0.f;
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  for (int64_t p = m.p_begin + m.pl; p < m.p_end; p += m.PL) {
-    float f[8];
-    unpack8(ld8(x + base + p * C), f);
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
+    bf16x8 v[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = fmaf(a[j], f[j], b[j]);
-      if (STATS) {
-        float ab = fabsf(y);
-        s[j] += y;
-        q[j] += y * y;
-        sa[j] += ab;
-        mx[j] = fmaxf(mx[j], ab);
-        nz[j] += (ab < near_zero) ? 1.f : 0.f;
-      }
-      f[j] = act ? silu_f(y) : y;
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p < m.p_end) v[u] = ld8(x + base + p * C);
     }
-    st8(out + base + p * C, pack8(f));
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p >= m.p_end) break;
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(a[j], f[j], b[j]);
+        if (STATS) {
+          float ab = fabsf(y);
+          s[j] += y;
+          q[j] += y * y;
+          sa[j] += ab;
+          mx[j] = fmaxf(mx[j], ab);
+          nz[j] += (ab < near_zero) ? 1.f : 0.f;
+        }
+        f[j] = act ? silu_f(y) : y;
+      }
+      st8(out + base + p * C, pack8(f));
+    }
   }
   if (STATS) {
 #pragma unroll
@@ -195,16 +218,29 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const bf16* __r
     ds[j] = db[j] = 0.f;
   }
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  for (int64_t p = m.p_begin + m.pl; p < m.p_end; p += m.PL) {
-    float f[8], g[8];
-    unpack8(ld8(x + base + p * C), f);
-    unpack8(ld8(dout + base + p * C), g);
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
+    bf16x8 vx[kUnroll], vg[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float gg = g[j];
-      if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
-      ds[j] += gg * f[j];
-      db[j] += gg;
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p < m.p_end) {
+        vx[u] = ld8(x + base + p * C);
+        vg[u] = ld8(dout + base + p * C);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (p0 + (int64_t)u * m.PL >= m.p_end) break;
+      float f[8], g[8];
+      unpack8(vx[u], f);
+      unpack8(vg[u], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gg = g[j];
+        if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
+        ds[j] += gg * f[j];
+        db[j] += gg;
+      }
     }
   }
 #pragma unroll
@@ -222,9 +258,19 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __re
                                                                 const void* __restrict__ gamma,
                                                                 const void* __restrict__ beta, int pdt,
                                                                 const float* __restrict__ dsdb, bf16* __restrict__ dx,
-                                                                float eps, int act, int HW, int C, int G) {
+                                                                const bf16* __restrict__ dres,
+                                                                float* __restrict__ colsum, float eps, int act, int HW,
+                                                                int C, int G) {
+  extern __shared__ float sm[];  // [C] when colsum
   const int n = blockIdx.y;
   Map m = make_map(C, HW);
+  if (colsum) {
+    for (int i = threadIdx.x; i < C; i += kThreads) sm[i] = 0.f;
+    __syncthreads();
+  }
+  float cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
   float a[8], b[8], c2[8], c3[8];
@@ -255,17 +301,42 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __re
     c3[j] = pc3;
   }
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  for (int64_t p = m.p_begin + m.pl; p < m.p_end; p += m.PL) {
-    float f[8], g[8];
-    unpack8(ld8(x + base + p * C), f);
-    unpack8(ld8(dout + base + p * C), g);
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
+    bf16x8 vx[kUnroll], vg[kUnroll], vr[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float gg = g[j];
-      if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
-      g[j] = fmaf(a[j], gg, fmaf(c2[j], f[j], c3[j]));
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p < m.p_end) {
+        vx[u] = ld8(x + base + p * C);
+        vg[u] = ld8(dout + base + p * C);
+        if (dres) vr[u] = ld8(dres + base + p * C);
+      }
     }
-    st8(dx + base + p * C, pack8(g));
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p >= m.p_end) break;
+      float f[8], g[8], r[8];
+      unpack8(vx[u], f);
+      unpack8(vg[u], g);
+      if (dres) unpack8(vr[u], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gg = g[j];
+        if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
+        float d = fmaf(a[j], gg, fmaf(c2[j], f[j], c3[j]));
+        if (dres) d += r[j];
+        g[j] = d;
+        cs[j] += d;
+      }
+      st8(dx + base + p * C, pack8(g));
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sm[m.c0 + j], cs[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += kThreads) atomicAdd(&colsum[i], sm[i]);
   }
 }
 
@@ -349,11 +420,13 @@ extern "C" int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* 
 }
 
 extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
-                                int param_dtype, const float* dsdb, void* dx, float eps, int act_silu, int N, int HW,
-                                int C, int G, vcd_stream_t stream) {
+                                int param_dtype, const float* dsdb, void* dx, const void* dres, float* dx_colsum,
+                                float eps, int act_silu, int N, int HW, int C, int G, vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
-  gn_bwd_apply_kernel<<<gn_grid(N, HW, C), kThreads, 0, as_stream(stream)>>>(
-      (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, eps, act_silu, HW, C, G);
+  if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, as_stream(stream)));
+  gn_bwd_apply_kernel<<<gn_grid(N, HW, C), kThreads, dx_colsum ? C * sizeof(float) : 0, as_stream(stream)>>>(
+      (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum,
+      eps, act_silu, HW, C, G);
   VCD_LAUNCH_CHECK();
   return 0;
 }

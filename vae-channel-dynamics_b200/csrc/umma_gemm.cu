@@ -288,7 +288,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 float f[8];
-                if (nt * BLOCK_N + ch * 32 + g * 8 >= p.Nout) continue;
+                if (nt * BLOCK_N + ch * 32 + g * 8 + 8 > p.Nout) continue;
                 unpack8(ld8(rp + g * 8), f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
@@ -296,9 +296,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
             bf16* op = p.out + off + ch * 32;
             const int col0 = nt * BLOCK_N + ch * 32;
+            if ((p.Nout & 7) == 0) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (col0 + g * 8 < p.Nout) st8(op + g * 8, pack8(v + g * 8));
+              for (int g = 0; g < 4; ++g)
+                if (col0 + g * 8 < p.Nout) st8(op + g * 8, pack8(v + g * 8));
+            } else {  // narrow outputs (e.g. decoder.conv_out, 3 channels): scalar stores
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.Nout) op[j] = __float2bfloat16_rn(v[j]);
+            }
           }
         }
       } else {

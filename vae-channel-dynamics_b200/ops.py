@@ -73,8 +73,11 @@ class TrackSlot:
         self.raw = torch.zeros(5 * channels, dtype=torch.float32, device=device)
         self.run = torch.zeros(5 * channels, dtype=torch.float32, device=device)
         self.scal = torch.zeros(3, dtype=torch.float64, device=device)
+        self.on_finalize = None  # monitor callback: records the order in which capture points fire
 
     def finalize(self, n_per_channel: int) -> None:
+        if self.on_finalize is not None:
+            self.on_finalize()
         call("vcd_stats_finalize", _p(self.raw), _p(self.run), _p(self.scal), int(n_per_channel), self.C, _st())
 
     def reset(self) -> None:
@@ -127,6 +130,34 @@ class PackedWeights:
         return self.wf, self.wd, self.bias
 
 
+def _workspace(fn: str, shape, impl: int, device):
+    if impl == IMPL_SIMT:
+        return None
+    nbytes = getattr(_lib.lib(), fn)(*shape)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
+
+
+# column sums of a gradient tensor, produced for free by the kernel that wrote it (vcd_gn_bwd_apply) and
+# consumed as the bias gradient of the conv that receives that tensor as dy
+_COLSUMS = {}
+
+
+def push_colsum(t: torch.Tensor, colsum: torch.Tensor) -> None:
+    # the entry keeps `t` alive, so its address cannot be recycled for another tensor while the entry exists
+    _COLSUMS[t.data_ptr()] = (t, colsum)
+
+
+def pop_colsum(t: torch.Tensor):
+    e = _COLSUMS.pop(t.data_ptr(), None)
+    if e is None or e[0].numel() != t.numel() or e[0].shape[-1] != t.shape[-1]:
+        return None
+    return e[1]
+
+
+def clear_colsums() -> None:
+    _COLSUMS.clear()
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, packs: PackedWeights, stride: int, pad_t: int, pad_l: int,
@@ -147,7 +178,8 @@ class _ConvFn(torch.autograd.Function):
         if residual is not None:
             residual = _nhwc(residual)
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
-        call("vcd_conv2d_fprop", _p(xs), _p(wf), _p(b32), _p(residual), _p(y), N, H, W, Cin, Cout, KH, KW, stride,
+        ws = _workspace("vcd_conv2d_fprop_ws_bytes", (N, H, W, Cin, Cout, KH, KW, stride), impl, x.device)
+        call("vcd_conv2d_fprop", _p(xs), _p(wf), _p(b32), _p(residual), _p(y), _p(ws), N, H, W, Cin, Cout, KH, KW, stride,
              pad_t, pad_l, Ho, Wo, planes, impl, _st())
         ctx.save_for_backward(xs, weight, bias)
         ctx.packs = packs
@@ -165,20 +197,22 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if planes:
                 dxp = torch.empty((N, 4, H // 2, W // 2, Cin), dtype=torch.bfloat16, device=dy.device)
-                call("vcd_conv2d_dgrad", _p(dy), _p(wf), _p(wd), _p(dxp), N, H, W, Cin, Cout, KH, KW, stride, pad_t,
+                call("vcd_conv2d_dgrad", _p(dy), _p(wf), _p(wd), _p(dxp), None, N, H, W, Cin, Cout, KH, KW, stride, pad_t,
                      pad_l, Ho, Wo, 1, impl, _st())
                 dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
                 call("vcd_planes_to_space", _p(dxp), _p(dx), N, H, W, Cin, _st())
             else:
                 dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
-                call("vcd_conv2d_dgrad", _p(dy), _p(wf), _p(wd), _p(dx), N, H, W, Cin, Cout, KH, KW, stride, pad_t,
+                ws = _workspace("vcd_conv2d_dgrad_ws_bytes", (N, H, W, Cin, Cout, KH, KW, stride), impl, dy.device)
+                call("vcd_conv2d_dgrad", _p(dy), _p(wf), _p(wd), _p(dx), _p(ws), N, H, W, Cin, Cout, KH, KW, stride, pad_t,
                      pad_l, Ho, Wo, 0, impl, _st())
         if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):
             dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
             db = None if bias is None else torch.empty_like(bias)
-            nbytes = _lib.lib().vcd_conv2d_wgrad_ws_bytes(Cin, Cout, KH, KW)
+            nbytes = _lib.lib().vcd_conv2d_wgrad_ws_bytes(N, H, W, Cin, Cout, KH, KW, stride)
             ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
-            call("vcd_conv2d_wgrad", _p(xs), _p(dy), _p(dw), _p(db), dtype_code(weight), _p(ws), N, H, W, Cin, Cout,
+            colsum = pop_colsum(dy) if db is not None else None
+            call("vcd_conv2d_wgrad", _p(xs), _p(dy), _p(dw), _p(db), _p(colsum), dtype_code(weight), _p(ws), N, H, W, Cin, Cout,
                  KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl, _st())
         dres = dy if ctx.has_res and ctx.needs_input_grad[3] else None
         return dx, dw, db, dres, None, None, None, None, None, None
@@ -195,9 +229,14 @@ def conv2d(x, weight, bias, packs, stride=1, pad_t=1, pad_l=1, out_hw=None, resi
 # GroupNorm (+SiLU) with fused statistics
 # ------------------------------------------------------------------------------------------
 class _GroupNormFn(torch.autograd.Function):
+    """GroupNorm [+SiLU].  With split=True the function also returns its input unchanged as a second output:
+    the block routes its skip connection through it, so backward receives the skip gradient explicitly and
+    adds it inside the dx kernel (no separate add pass) while emitting the column sums of dx (= the bias
+    gradient of the conv that produced x)."""
+
     @staticmethod
     def forward(ctx, x, gamma, beta, groups: int, eps: float, act: bool, slot_in: Optional[TrackSlot],
-                slot_out: Optional[TrackSlot]):
+                slot_out: Optional[TrackSlot], split: bool):
         x = _nhwc(x)
         N, C = x.shape[0], x.shape[-1]
         hw = x.numel() // (N * C)
@@ -215,13 +254,17 @@ class _GroupNormFn(torch.autograd.Function):
             slot_out.finalize(N * hw)
         ctx.save_for_backward(x, sums, gamma, beta)
         ctx.cfg = (N, hw, C, groups, float(eps), 1 if act else 0)
+        if split:
+            return out, x.view(x.shape)
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dres=None):
         x, sums, gamma, beta = ctx.saved_tensors
         N, hw, C, G, eps, act = ctx.cfg
         dout = _nhwc(dout)
+        if dres is not None:
+            dres = _nhwc(dres)
         g, b = gamma.detach(), beta.detach()
         pdt = dtype_code(g)
         dsdb = torch.empty(N * C * 2, dtype=torch.float32, device=x.device)
@@ -229,16 +272,18 @@ class _GroupNormFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            call("vcd_gn_bwd_apply", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), _p(dx), eps, act, N, hw,
-                 C, G, _st())
+            colsum = torch.empty(C, dtype=torch.float32, device=x.device)
+            call("vcd_gn_bwd_apply", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), _p(dx), _p(dres),
+                 _p(colsum), eps, act, N, hw, C, G, _st())
+            push_colsum(dx, colsum)
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(beta)
         call("vcd_gn_param_grad", _p(sums), _p(dsdb), _p(dgamma), _p(dbeta), pdt, eps, N, hw, C, G, _st())
-        return dx, dgamma, dbeta, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
-def group_norm(x, gamma, beta, groups, eps, act, slot_in=None, slot_out=None):
-    return _GroupNormFn.apply(x, gamma, beta, groups, eps, act, slot_in, slot_out)
+def group_norm(x, gamma, beta, groups, eps, act, slot_in=None, slot_out=None, split=False):
+    return _GroupNormFn.apply(x, gamma, beta, groups, eps, act, slot_in, slot_out, split)
 
 
 # ------------------------------------------------------------------------------------------

@@ -66,6 +66,7 @@ class ActivityMonitor:
         self.extended_data_by_step = defaultdict(dict)   # variance / near-zero fraction / max-abs (north star)
         self.hooks: List[Any] = []
         self._targets: Dict[str, _Target] = {}
+        self._fired: List[str] = []
         self.near_zero_threshold = float(self.config.get("near_zero_threshold", 0.0))
         if self.config.get("enabled", False):
             self._register_hooks()
@@ -89,8 +90,14 @@ class ActivityMonitor:
     def _slot_for(self, tgt: _Target, channels: int, device) -> ops.TrackSlot:
         if tgt.slot is None or tgt.slot.C != channels or tgt.slot.raw.device != device:
             tgt.slot = ops.TrackSlot(channels, device, self.near_zero_threshold)
+            tgt.slot.on_finalize = lambda ident=tgt.identifier: self._note_fired(ident)
             tgt.channels = channels
         return tgt.slot
+
+    def _note_fired(self, ident: str):
+        """The reference's buffer is keyed in first-fire order (monitor.py:101); step() reports in that order."""
+        if ident not in self._fired:
+            self._fired.append(ident)
 
     def _register_hooks(self):
         self.remove_hooks()
@@ -169,6 +176,7 @@ class ActivityMonitor:
                     slot = monitor._slot_for(tgt, t.shape[1], t.device)
                     ops.chan_stats(t.detach(), slot)
                 if full_map:
+                    monitor._note_fired(tgt.identifier)
                     if tgt.first_map is None:
                         d = t.detach()
                         tgt.first_map = (d.float() if d.dtype == torch.bfloat16 else d.clone()).cpu()
@@ -222,7 +230,9 @@ class ActivityMonitor:
         processed: Dict[str, Dict[str, Any]] = {}
         extended: Dict[str, Dict[str, Any]] = {}
         gathered = self._gather()
-        for ident, tgt in self._targets.items():
+        order = [i for i in self._fired if i in self._targets]
+        for ident in order:
+            tgt = self._targets[ident]
             entry: Dict[str, Any] = {}
             run, scal = gathered.get(ident, (None, None))
             forwards = float(scal[2]) if scal is not None else 0.0
@@ -261,6 +271,7 @@ class ActivityMonitor:
             self.extended_data_by_step[global_step] = extended
             logger.info(f"ActivityMonitor collected and processed data for step {global_step}.")
         self.hook_collected_buffer.clear()
+        self._fired = []
         self._mark_gamma_sync()
         return wandb_metrics
 

@@ -90,9 +90,11 @@ class B200GroupNorm(nn.GroupNorm):
         self._track_in: Optional[ops.TrackSlot] = None
         self._track_out: Optional[ops.TrackSlot] = None
 
-    def forward(self, x, act: bool = False):
+    def forward(self, x, act: bool = False, split: bool = False):
         y = ops.group_norm(_phys(x), self.weight, self.bias, self.num_groups, self.eps, act,
-                           self._track_in, self._track_out)
+                           self._track_in, self._track_out, split)
+        if split:   # (normalised, input routed through for the block's skip connection)
+            return _logi(y[0]), _logi(y[1])
         return _logi(y)
 
 
@@ -111,11 +113,13 @@ class B200Linear(nn.Linear):
         return y.reshape(N, T, -1)
 
 
-def _norm_act(norm: B200GroupNorm, x):
-    """GroupNorm followed by SiLU; unfused only when a foreign hook must observe the pre-activation."""
+def _norm_act(norm: B200GroupNorm, x, split: bool = False):
+    """GroupNorm followed by SiLU; unfused only when a foreign hook must observe the pre-activation.
+    split=True additionally returns the tensor the block's skip connection must use (see ops._GroupNormFn)."""
     if _hooked(norm):
-        return _logi(ops.silu(_phys(norm(x))))
-    return norm(x, act=True)
+        h = _logi(ops.silu(_phys(norm(x))))
+        return (h, x) if split else h
+    return norm(x, act=True, split=split)
 
 
 class ResnetBlock2D(nn.Module):
@@ -129,7 +133,8 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = B200Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h = self.conv1(_norm_act(self.norm1, x))
+        h, x = _norm_act(self.norm1, x, split=True)
+        h = self.conv1(h)
         h = _norm_act(self.norm2, h)
         sc = x if self.conv_shortcut is None else self.conv_shortcut(x)
         if _hooked(self.conv2):
@@ -151,7 +156,10 @@ class Attention(nn.Module):
     def forward(self, x):
         N, C, H, W = x.shape
         tokens = _phys(x).reshape(N, H * W, C)                      # physical [N, T, C]
-        h = _phys(self.group_norm(_logi(tokens)))                   # GroupNorm sees logical [N, C, T]
+        if _hooked(self.group_norm):
+            h = _phys(self.group_norm(_logi(tokens)))               # GroupNorm sees logical [N, C, T]
+        else:
+            h, tokens = (_phys(t) for t in self.group_norm(_logi(tokens), split=True))
         q, k, v = self.to_q(h), self.to_k(h), self.to_v(h)
         o = ops.attention_core(q, k, v)
         o = self.to_out[0](o, residual=tokens)
@@ -357,6 +365,7 @@ class B200AutoencoderKL(nn.Module):
         if x.dim() != 4:
             raise VcdError(f"encode expects [N, 3, H, W], got {tuple(x.shape)}")
         self._sync_gamma_if_pending()
+        ops.clear_colsums()
         moments = self.quant_conv(self.encoder(x))
         dist = DiagonalGaussianDistribution(moments)
         return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
