@@ -232,10 +232,10 @@ def conv_roofline(torch, vcd, R, B, peaks):
         def run(i):
             y = ops.conv2d(xs[i % nbuf], w, bias, packs, stride=1, pad_t=pad, pad_l=pad)
             y.backward(g)
-        for i in range(2):
+        for i in range(3):
             run(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 4
+        iters = 5
         torch.cuda.synchronize()
         e0.record()
         for i in range(iters):

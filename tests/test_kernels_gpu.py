@@ -52,6 +52,13 @@ def test_conv_simt_small_channels(vcd, cin, cout, k):
     _conv_case(vcd, 2, 12, 10, cin, cout, k, 1, vcd._lib.IMPL_SIMT)
 
 
+@pytest.mark.parametrize("cin,cout", [(3, 128), (128, 3), (512, 8), (4, 512), (128, 64)])
+def test_conv_small_channels_on_tcgen05(vcd, cin, cout):
+    """the small-channel layers of the VAE on the tcgen05 kernel: narrow-N implicit GEMM / im2col patch + GEMM"""
+    _conv_case(vcd, 2, 12, 10, cin, cout, 3, 1, vcd._lib.IMPL_UMMA if (cin, cout) != (128, 64) else vcd._lib.IMPL_AUTO)
+    _conv_case(vcd, 1, 16, 16, cin, cout, 3, 1, vcd._lib.IMPL_AUTO)
+
+
 def test_conv_simt_stride2_and_residual(vcd):
     _conv_case(vcd, 2, 12, 8, 16, 16, 3, 2, vcd._lib.IMPL_SIMT)
     _conv_case(vcd, 1, 6, 6, 32, 32, 3, 1, vcd._lib.IMPL_SIMT, residual=True)
@@ -80,6 +87,30 @@ def test_groupnorm_silu_fwd_bwd(vcd, C, H, W, act):
     assert rel_err(nchw(xp.grad), xr.grad) < TOL
     assert rel_err(gamma.grad, gr.grad) < TOL
     assert rel_err(beta.grad, br.grad) < TOL
+
+
+def test_groupnorm_split_skip_gradient_and_colsum(vcd):
+    """split=True: the skip-connection gradient is added inside the dx kernel and the column sums of dx
+    (bias gradient of the producing conv) come out of the same pass."""
+    ops = vcd.ops
+    N, C, H, W, G = 2, 128, 12, 12, 32
+    x = bf16_round(torch.randn(N, C, H, W, device="cuda"))
+    gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_()
+    beta = (torch.randn(C, device="cuda") * 0.1).requires_grad_()
+    xr = x.clone().requires_grad_()
+    ref = _gn_ref(xr, gamma.detach(), beta.detach(), G, 1e-6, True)
+    go, gs = bf16_round(torch.randn_like(ref)), bf16_round(torch.randn_like(ref))
+    (ref * go).sum().add((xr * gs).sum()).backward()
+    xp = nhwc(x).requires_grad_()
+    seen = []
+    xp.register_hook(lambda g: seen.append((g, ops.pop_colsum(g))))   # what a producing conv's backward receives
+    y, xid = ops.group_norm(xp, gamma, beta, G, 1e-6, True, None, None, True)
+    assert torch.equal(xid, xp)
+    torch.autograd.backward([y, xid], [nhwc(go), nhwc(gs)])
+    assert rel_err(nchw(xp.grad), xr.grad) < TOL
+    g, cs = seen[0]
+    assert cs is not None and rel_err(cs, xr.grad.sum(dim=[0, 2, 3])) < TOL
+    assert ops.pop_colsum(g) is None
 
 
 def test_groupnorm_bf16_params(vcd):

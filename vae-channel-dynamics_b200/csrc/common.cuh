@@ -42,26 +42,38 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 int vcd_num_sms();
 
 // ---- device helpers ---------------------------------------------------------------
+// eight bf16 values moved as ONE 128-bit access (LDG.E.128 / STG.E.128; a struct of bfloat162 is split
+// into four 32-bit accesses by nvcc, which quarters the bytes per L2 request)
 struct alignas(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  uint4 u;
 };
 
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w);
+  return __bfloat1622float2(h);
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  float2 t;
+  t = bf2_to_f2(p.u.x); f[0] = t.x; f[1] = t.y;
+  t = bf2_to_f2(p.u.y); f[2] = t.x; f[3] = t.y;
+  t = bf2_to_f2(p.u.z); f[4] = t.x; f[5] = t.y;
+  t = bf2_to_f2(p.u.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
   bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  p.u = make_uint4(f2_to_bf2(f[0], f[1]), f2_to_bf2(f[2], f[3]), f2_to_bf2(f[4], f[5]), f2_to_bf2(f[6], f[7]));
   return p;
 }
-__device__ __forceinline__ bf16x8 ld8(const bf16* ptr) { return *reinterpret_cast<const bf16x8*>(ptr); }
-__device__ __forceinline__ void st8(bf16* ptr, const bf16x8& v) { *reinterpret_cast<bf16x8*>(ptr) = v; }
+__device__ __forceinline__ bf16x8 ld8(const bf16* ptr) {
+  bf16x8 p;
+  p.u = *reinterpret_cast<const uint4*>(ptr);
+  return p;
+}
+__device__ __forceinline__ void st8(bf16* ptr, const bf16x8& v) { *reinterpret_cast<uint4*>(ptr) = v.u; }
 
 __device__ __forceinline__ float load_param(const void* p, int dtype, int i) {
   return dtype == VCD_F32 ? reinterpret_cast<const float*>(p)[i]

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) conv_small_out_kernel(const bf16* __restr
                                                              const float* __restrict__ bias, bf16* __restrict__ out, int N,
                                                              int Hin, int Win, int Ci, int Hout, int Wout, int Co,
                                                              int stride, int transposed, Taps taps) {
-  extern __shared__ bf16 sw[];  // [tap][Co][Ci]
+  extern __shared__ __align__(16) bf16 sw[];  // [tap][Co][Ci]
   const int wn = taps.n * Co * Ci;
   for (int i = threadIdx.x; i < wn; i += blockDim.x) sw[i] = wt[i];
   __syncthreads();
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) conv_small_out_kernel(const bf16* __restr
         for (int o = 0; o < 8; ++o) {
           if (o < Co) {
             float g[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(wp + o * Ci + i), g);
+            unpack8(ld8(wp + o * Ci + i), g);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[o] = fmaf(f[j], g[j], acc[o]);
           }

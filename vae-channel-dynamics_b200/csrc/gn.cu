@@ -13,7 +13,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kIters = 32;  // pixels per thread per block
+constexpr int kIters = 64;  // pixels per thread per block
 
 constexpr int kUnroll = 4;
 
@@ -34,15 +34,20 @@ __device__ __forceinline__ Map make_map(int C, int HW) {
   return m;
 }
 
-__device__ __forceinline__ void group_mean_rstd(const double* sums, int n, int G, int g, double cnt, float eps,
-                                                float& mean, float& rstd) {
-  double s = sums[((int64_t)n * G + g) * 2], q = sums[((int64_t)n * G + g) * 2 + 1];
-  double mu = s / cnt;
-  double var = q / cnt - mu * mu;
-  if (var < 0.0) var = 0.0;
-  mean = (float)mu;
-  rstd = (float)(1.0 / sqrt(var + (double)eps));
+// mean / rstd of every group of image n, computed once per block (fp64 sums -> fp32) into shared memory
+__device__ __forceinline__ void load_group_stats(const double* sums, int n, int G, double cnt, float eps, float* s_mean,
+                                                 float* s_rstd) {
+  for (int g = threadIdx.x; g < G; g += kThreads) {
+    double s = sums[((int64_t)n * G + g) * 2], q = sums[((int64_t)n * G + g) * 2 + 1];
+    double mu = s / cnt;
+    double var = q / cnt - mu * mu;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mu;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
 }
+constexpr int kMaxGroups = 64;
 
 // ---------------------------------------------------------------- pass 1: group sums (+ input stats)
 template <bool STATS>
@@ -130,14 +135,14 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const bf16* __restri
   }
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+  load_group_stats(sums, n, G, cnt, eps, s_mean, s_rstd);
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     int c = m.c0 + j;
-    float mean, rstd;
-    group_mean_rstd(sums, n, G, c / D, cnt, eps, mean, rstd);
-    a[j] = rstd * load_param(gamma, pdt, c);
-    b[j] = load_param(beta, pdt, c) - mean * a[j];
+    a[j] = s_rstd[c / D] * load_param(gamma, pdt, c);
+    b[j] = load_param(beta, pdt, c) - s_mean[c / D] * a[j];
   }
   float s[8], q[8], sa[8], mx[8], nz[8];
 #pragma unroll
@@ -207,14 +212,14 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const bf16* __r
   __syncthreads();
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+  load_group_stats(sums, n, G, cnt, eps, s_mean, s_rstd);
   float a[8], b[8], ds[8], db[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     int c = m.c0 + j;
-    float mean, rstd;
-    group_mean_rstd(sums, n, G, c / D, cnt, eps, mean, rstd);
-    a[j] = rstd * load_param(gamma, pdt, c);
-    b[j] = load_param(beta, pdt, c) - mean * a[j];
+    a[j] = s_rstd[c / D] * load_param(gamma, pdt, c);
+    b[j] = load_param(beta, pdt, c) - s_mean[c / D] * a[j];
     ds[j] = db[j] = 0.f;
   }
   const int64_t base = (int64_t)n * HW * C + m.c0;
@@ -273,6 +278,8 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __re
   for (int j = 0; j < 8; ++j) cs[j] = 0.f;
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+  load_group_stats(sums, n, G, cnt, eps, s_mean, s_rstd);
   float a[8], b[8], c2[8], c3[8];
   int prev_g = -1;
   float pc2 = 0.f, pc3 = 0.f;
@@ -280,8 +287,7 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __re
   for (int j = 0; j < 8; ++j) {
     int c = m.c0 + j;
     int g = c / D;
-    float mean, rstd;
-    group_mean_rstd(sums, n, G, g, cnt, eps, mean, rstd);
+    const float mean = s_mean[g], rstd = s_rstd[g];
     a[j] = rstd * load_param(gamma, pdt, c);
     b[j] = load_param(beta, pdt, c) - mean * a[j];
     if (g != prev_g) {
@@ -348,8 +354,11 @@ __global__ void gn_param_grad_kernel(const double* __restrict__ sums, const floa
   const double cnt = (double)D * (double)HW;
   float dg = 0.f, dbv = 0.f;
   for (int n = 0; n < N; ++n) {
-    float mean, rstd;
-    group_mean_rstd(sums, n, G, c / D, cnt, eps, mean, rstd);
+    const int g = c / D;
+    double sg = sums[((int64_t)n * G + g) * 2], qg = sums[((int64_t)n * G + g) * 2 + 1];
+    double mu = sg / cnt, var = qg / cnt - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
     float ds = dsdb[((int64_t)n * C + c) * 2], db = dsdb[((int64_t)n * C + c) * 2 + 1];
     dg += (ds - mean * db) * rstd;
     dbv += db;
@@ -364,7 +373,7 @@ int check_shape(int C, int G) {
     vcd_set_error("GroupNorm kernels need C %% 8 == 0 and C/8 a divisor of 256 (got C=%d)", C);
     return -1;
   }
-  if (G <= 0 || C % G != 0) {
+  if (G <= 0 || C % G != 0 || G > kMaxGroups) {
     vcd_set_error("GroupNorm: C=%d not divisible by G=%d", C, G);
     return -1;
   }

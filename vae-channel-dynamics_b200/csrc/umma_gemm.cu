@@ -359,6 +359,12 @@ EncodeTiledFn get_encode() {
 
 int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int P, int N, int box_c, int box_w, int box_h,
                  int box_n) {
+  // the encode is a driver-API call: autograd's backward threads may not have bound the primary context yet
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     vcd_set_error("cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
