@@ -1,0 +1,150 @@
+"""CPU: the C-ABI library loads and exports every symbol include/vcd.h declares (no compute calls without a
+GPU), the ctypes table matches the header's arity, the host modules keep the reference's interface, and the
+product path fails loudly — never falls back — when there is no CUDA device."""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_decls():
+    src = open(os.path.join(ROOT, "include", "vcd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*)\s+(vcd_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        decls[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return decls
+
+
+def test_library_exports_every_declared_symbol(vcd):
+    decls = _header_decls()
+    assert len(decls) >= 35
+    lib = vcd._lib.lib()
+    for name in decls:
+        assert hasattr(lib, name), f"{name} declared in include/vcd.h but not exported by libvcd_b200.so"
+    assert lib.vcd_version() >= 100
+    assert lib.vcd_last_error() is not None
+
+
+def test_ctypes_table_matches_header(vcd):
+    decls = _header_decls()
+    sigs = vcd._lib.SIGNATURES
+    assert set(sigs) == set(decls), set(sigs) ^ set(decls)
+    for name, (_, argtypes) in sigs.items():
+        assert len(argtypes) == decls[name], (name, len(argtypes), decls[name])
+
+
+def test_library_is_sm100a_tcgen05_code():
+    import subprocess
+    lib = os.path.join(ROOT, "vae-channel-dynamics_b200", "libvcd_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STG.E.128", "LDG.E.128"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_module_tree_is_diffusers_compatible(vcd):
+    from oracle.torch_vae import build_oracle
+    model = vcd.B200AutoencoderKL()
+    oracle = build_oracle(1)
+    assert [n for n, _ in model.named_parameters()] == [n for n, _ in oracle.named_parameters()]
+    assert [tuple(p.shape) for p in model.parameters()] == [tuple(p.shape) for p in oracle.parameters()]
+    model.load_state_dict(oracle.state_dict())
+    assert model.config.scaling_factor == 0.13025 and model.config["latent_channels"] == 4
+    gns = [m for m in model.modules() if isinstance(m, nn.GroupNorm)]          # classifier.py:56
+    assert len(gns) == 52 and all(isinstance(m.weight, nn.Parameter) for m in gns)
+    assert sum(isinstance(m, (nn.Conv2d, nn.Linear)) for m in model.modules()) == 64 + 8   # train.py:38
+
+
+def test_save_and_from_pretrained_roundtrip(vcd, tmp_path):
+    torch.manual_seed(3)
+    m = vcd.B200AutoencoderKL()
+    m.save_pretrained(str(tmp_path / "vae"))
+    assert sorted(os.listdir(tmp_path / "vae")) == ["config.json", "diffusion_pytorch_model.safetensors"]
+    m2 = vcd.B200AutoencoderKL.from_pretrained(str(tmp_path / "vae"), torch_dtype=torch.bfloat16)
+    assert m2.dtype == torch.bfloat16
+    for (n, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a.to(torch.bfloat16), b), n
+    m3 = vcd.B200AutoencoderKL.from_pretrained("random-init:7")
+    m4 = vcd.B200AutoencoderKL.from_pretrained("random-init:7")
+    assert torch.equal(m3.encoder.conv_in.weight, m4.encoder.conv_in.weight)
+    with pytest.raises(vcd.VcdError):
+        vcd.B200AutoencoderKL.from_pretrained("stabilityai/sdxl-vae")       # no network, no silent random weights
+
+
+def test_host_modules_keep_reference_interface(vcd):
+    vcd.add_src_to_path()
+    from models.sdxl_vae_wrapper import SDXLVAEWrapper
+    from tracking.monitor import ActivityMonitor
+    from tracking.deadneuron import DeadNeuronTracker
+    from classification.classifier import RegionClassifier
+    from intervention.nudger import InterventionHandler
+    assert list(inspect.signature(SDXLVAEWrapper.__init__).parameters) == ["self", "pretrained_model_name_or_path", "torch_dtype"]
+    assert list(inspect.signature(SDXLVAEWrapper.forward).parameters) == ["self", "pixel_values", "sample_posterior"]
+    for meth in ("add_hooks", "remove_hooks", "get_captured_activations", "clear_captured_activations", "encode", "decode"):
+        assert hasattr(SDXLVAEWrapper, meth)
+    for meth in ("step", "get_data_for_step", "export_all_processed_data_to_records", "remove_hooks", "_get_layer"):
+        assert hasattr(ActivityMonitor, meth)
+    assert list(inspect.signature(DeadNeuronTracker.__init__).parameters) == [
+        "self", "target_layer_classes", "target_layer_names_for_raw_weights", "threshold", "mean_percentage", "dead_type"]
+    assert list(inspect.signature(RegionClassifier.classify).parameters) == ["self", "tracked_data_for_step", "global_step"]
+    assert list(inspect.signature(InterventionHandler.intervene).parameters) == ["self", "classification_results", "global_step"]
+    w = SDXLVAEWrapper("random-init:42")
+    assert w.scaling_factor == 0.13025 and isinstance(w.vae, vcd.B200AutoencoderKL)
+    # classifier map: 52 GroupNorms -> plain + 'vae.'-prefixed keys (classifier.py:43-81)
+    clf = RegionClassifier(w.vae, {"enabled": True, "threshold": 0.2})
+    assert len(clf._layer_to_param_map) == 104
+    assert clf._lookup_param_info("vae.encoder.down_blocks.0.resnets.0.norm1.output") == \
+        ("encoder.down_blocks.0.resnets.0.norm1.weight", 128)
+    assert clf._lookup_param_info("vae.encoder.conv_in.output") is None
+    assert clf.classify({}, 1) == {} and RegionClassifier(w.vae, {"enabled": False}).classify({"x": {}}, 1) == {}
+    # nudger guards (nudger.py:89-103) need no device
+    ih = InterventionHandler(w.vae, {"enabled": True, "strategy": "gentle_nudge_groupnorm_scale", "intervention_interval": 10})
+    ih.intervene({}, 10)
+    ih.intervene({"k": {"param_name_scale": "nope.weight", "inactive_channel_indices": [0]}}, 10)
+    assert ih.num_nudges_applied == 0 and ih._get_parameter("decoder.conv_norm_out.weight") is not None
+    # monitor registration resolves the shipped config names through a DDP-style '.module' wrapper (monitor.py:41-54)
+    class Wrap(nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+    mon = ActivityMonitor(Wrap(w), {"enabled": True, "track_interval": 20, "target_layers": [
+        {"name": "vae.encoder.conv_in", "capture_point": "output", "metrics": ["mean_abs_activation_per_channel"]},
+        {"name": "vae.decoder.up_blocks.1.resnets.0.norm1", "capture_point": "input", "metrics": ["full_activation_map"]},
+        {"name": "vae.does.not.exist", "capture_point": "output"}]})
+    assert len(mon.hooks) == 2 and mon.step(7) == {} and mon.get_data_for_step(20) == {}
+    mon.remove_hooks()
+    assert mon.hooks == [] and not w.vae.encoder.conv_in._forward_hooks
+    assert ActivityMonitor(w, {"enabled": False}).step(20) == {}
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(vcd):
+    m = vcd.B200AutoencoderKL()
+    with pytest.raises(vcd.VcdError, match="CUDA"):
+        m.encode(torch.zeros(1, 3, 32, 32))
+    vcd.add_src_to_path()
+    from classification.classifier import RegionClassifier
+    from tracking.deadneuron import DeadNeuronTracker
+    clf = RegionClassifier(m, {"enabled": True, "threshold": 0.2})
+    with pytest.raises(vcd.VcdError):
+        clf.classify({"encoder.conv_norm_out.output": {"mean_abs_activation_per_channel": np.zeros(512, np.float32)}}, 1)
+    trk = DeadNeuronTracker((nn.Conv2d,), [], 1e-3, 0.1, "both")
+    with pytest.raises(vcd.VcdError):
+        trk.get_percentage(torch.zeros(8))
+
+
+def test_bench_flop_model_matches_survey():
+    import bench
+    assert len(bench.conv_layers(512)) == 64
+    total, conv, attn = bench.train_flops_per_image(512)
+    assert abs(conv / 1e9 - 3545.3) < 0.1 and abs(attn / 1e9 - 85.9) < 0.1 and abs(total / 1e12 - 10.89) < 0.01
+    total, conv, attn = bench.train_flops_per_image(256)
+    assert abs(total / 1e12 - 2.685) < 0.001

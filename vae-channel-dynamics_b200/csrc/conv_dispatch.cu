@@ -68,6 +68,14 @@ void set_form1_desc(UmmaParams& p, int block_n) {
   p.idesc = make_idesc(block_n, 1, 1);
 }
 int pick_block_n(int n) { return (n % 256 == 0) ? 256 : 128; }
+// split-K factor: the largest split that keeps tiles <= 2 full waves of the persistent grid (a partial third
+// wave costs a whole wave), but never more splits than K steps
+int pick_splits(int base_tiles, int k_tiles) {
+  const int target = 2 * vcd_num_sms();
+  int splits = base_tiles >= target ? 1 : target / base_tiles;
+  if (splits > k_tiles) splits = k_tiles;
+  return splits < 1 ? 1 : splits;
+}
 
 // taps of a conv seen from the OUTPUT pixel grid, reading the (possibly parity-plane) input
 void fill_fprop_taps(UmmaParams& p, int KH, int KW, int stride, int pad_t, int pad_l, int rows_per_tap) {
@@ -206,9 +214,7 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
   p.batches = 1;
   p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int base_tiles = p.ntaps * p.m_tiles * p.n_tiles;
-  int splits = (2 * vcd_num_sms() + base_tiles - 1) / base_tiles;
-  if (splits > p.k_tiles) splits = p.k_tiles;
-  if (splits < 1) splits = 1;
+  int splits = pick_splits(base_tiles, p.k_tiles);
   p.k_per_split = (p.k_tiles + splits - 1) / splits;
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
   set_form1_desc(p, bn);
@@ -318,9 +324,7 @@ int gemm_tn_impl(const void* A, const void* B, float* acc, int batch, int M, int
   p.batches = reduce_batch ? 1 : batch;
   p.k_tiles = reduce_batch ? p.tiles_w * batch : p.tiles_w;
   const int base_tiles = p.batches * p.m_tiles * p.n_tiles;
-  int splits = (vcd_num_sms() + base_tiles - 1) / base_tiles;
-  if (splits > p.k_tiles) splits = p.k_tiles;
-  if (splits < 1) splits = 1;
+  int splits = pick_splits(base_tiles, p.k_tiles);
   p.k_per_split = (p.k_tiles + splits - 1) / splits;
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
   set_form1_desc(p, bn);
