@@ -32,7 +32,7 @@ UNIT = "images/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--track-interval", type=int, default=20)
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph: the per-op path unchanged train.py gets (DDP for N>1)")
     ap.add_argument("--quick", action="store_true", help="profiling aid: warm-up as given, no e2e/roofline/cpu legs")
     return ap.parse_args()
 
@@ -314,7 +315,7 @@ def main():
     wrapper = SDXLVAEWrapper("random-init:42", torch_dtype=torch.bfloat16).to(dev)
     plant_dead_channels(wrapper.vae, torch)
     model = wrapper
-    if world > 1:
+    if world > 1 and args.eager:
         model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[local_rank], gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(wrapper.parameters(), lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8, fused=True)
     tcfg = {"enabled": True, "track_interval": args.track_interval,
@@ -333,14 +334,24 @@ def main():
     resident = [h.to(dev) for h in host]
     state = {"gs": 0, "nudged": 0, "inactive": 0}
     kl_weight = 1e-6
+    launches_per_step = [0]
+
+    graphed = None
+    if not args.eager:   # forward + loss + backward captured once in a CUDA graph (vcd_b200.GraphedVAEStep)
+        graphed = vcd_b200.GraphedVAEStep(wrapper, kl_weight, resident[0])
 
     def train_step(x):
-        out = model(x, sample_posterior=True)
-        total, rec, kl = vcd_b200.vae_loss(out, x, kl_weight)
-        total.backward()
-        torch.nn.utils.clip_grad_norm_(wrapper.parameters(), 1.0)
-        opt.step()
-        opt.zero_grad(set_to_none=True)
+        if graphed is not None:
+            total, rec, kl = graphed.step(x)
+            torch.nn.utils.clip_grad_norm_(wrapper.parameters(), 1.0)
+            opt.step()
+        else:
+            out = model(x, sample_posterior=True)
+            total, rec, kl = vcd_b200.vae_loss(out, x, kl_weight)
+            total.backward()
+            torch.nn.utils.clip_grad_norm_(wrapper.parameters(), 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
         state["gs"] += 1
         gs = state["gs"]
         if gs % args.track_interval == 0:                 # train.py:308-319 cadence
@@ -373,11 +384,12 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        launches_per_step[0] = (vcd_b200._lib.launches - l0) / K + (graphed.launches_per_replay if graphed is not None else 0)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
-        return ms, vcd_b200._lib.launches - l0, float(last)
+        return ms, int(launches_per_step[0] * K), float(last)
 
     n_warm = args.warmup if args.quick else max(3, args.warmup)
     for i in range(n_warm):
@@ -413,6 +425,7 @@ def main():
                                    f"classify+nudge every {args.track_interval} steps, random-init SDXL-VAE seed 42, bf16 weights",
                        "resolution": R, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "optimizer": "clip_grad_norm 1.0 + AdamW (torch fused) as in train.py:301-304",
+                       "execution": "eager per-op launches" if args.eager else "forward+loss+backward replayed from one CUDA graph (GraphedVAEStep); clip/AdamW/tracker eager",
                        "l2": "4 distinct input batches rotated; every activation tensor exceeds the 126 MB L2 at this size",
                        "train_tflop_per_image": fl_img / 1e12,
                        "step_mfu_of_sustained_peak": (value / world) * fl_img / 1e12 / peak_t,

@@ -34,6 +34,31 @@ __device__ __forceinline__ Map make_map(int C, int HW) {
   return m;
 }
 
+
+// Block-wide per-channel reduction without atomics: thread (pl, v) deposits its 8 channels x K partials at
+// red[k][j][pl][v] (v fastest: conflict-free), then one thread per channel sums the PL pixel lanes.
+template <int K>
+__device__ __forceinline__ void deposit(float* red, const Map& m, const float (*vals)[8]) {
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[((k * 8 + j) * m.PL + m.pl) * m.V + m.v] = vals[k][j];
+}
+__device__ __forceinline__ float lane_sum(const float* red, const Map& m, int k, int c) {
+  const int v = c >> 3, j = c & 7;
+  const float* p = red + ((k * 8 + j) * m.PL) * m.V + v;
+  float t = 0.f;
+  for (int q = 0; q < m.PL; ++q) t += p[q * m.V];
+  return t;
+}
+__device__ __forceinline__ float lane_max(const float* red, const Map& m, int k, int c) {
+  const int v = c >> 3, j = c & 7;
+  const float* p = red + ((k * 8 + j) * m.PL) * m.V + v;
+  float t = 0.f;
+  for (int q = 0; q < m.PL; ++q) t = fmaxf(t, p[q * m.V]);
+  return t;
+}
+
 // mean / rstd of every group of image n, computed once per block (fp64 sums -> fp32) into shared memory
 __device__ __forceinline__ void load_group_stats(const double* sums, int n, int G, double cnt, float eps, float* s_mean,
                                                  float* s_rstd) {
@@ -54,14 +79,15 @@ template <bool STATS>
 __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ sums,
                                                             float* __restrict__ cstats, float near_zero, int HW,
                                                             int C, int G) {
-  extern __shared__ float sm[];  // [C][2] (+ [C][3] when STATS: sumabs, max, nz)
+  extern __shared__ float red[];  // [K][8][PL][V] with K = 2 (5 when STATS), then [C][2] channel sums
+  constexpr int K = STATS ? 5 : 2;
   const int n = blockIdx.y;
   Map m = make_map(C, HW);
-  for (int i = threadIdx.x; i < C * (STATS ? 5 : 2); i += kThreads) sm[i] = 0.f;
-  __syncthreads();
-  float s[8], q[8], sa[8], mx[8], nz[8];
+  float acc[K][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0.f;
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
   const bf16* xb = x + (int64_t)n * HW * C + m.c0;
   for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
     bf16x8 v[kUnroll];
@@ -77,25 +103,30 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restri
       unpack8(v[u], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        q[j] += f[j] * f[j];
+        acc[0][j] += f[j];
+        acc[1][j] += f[j] * f[j];
         if (STATS) {
           float a = fabsf(f[j]);
-          sa[j] += a;
-          mx[j] = fmaxf(mx[j], a);
-          nz[j] += (a < near_zero) ? 1.f : 0.f;
+          acc[2][j] += a;
+          acc[3][j] = fmaxf(acc[3][j], a);
+          acc[4][j] += (a < near_zero) ? 1.f : 0.f;
         }
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[(m.c0 + j) * 2], s[j]);
-    atomicAdd(&sm[(m.c0 + j) * 2 + 1], q[j]);
+  deposit<K>(red, m, acc);
+  __syncthreads();
+  float* chan = red + K * 8 * kThreads;  // [C][2]
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    float s = lane_sum(red, m, 0, c), q = lane_sum(red, m, 1, c);
+    chan[c * 2] = s;
+    chan[c * 2 + 1] = q;
     if (STATS) {
-      atomicAdd(&sm[2 * C + (m.c0 + j) * 3], sa[j]);
-      atomic_max_nonneg(&sm[2 * C + (m.c0 + j) * 3 + 1], mx[j]);
-      atomicAdd(&sm[2 * C + (m.c0 + j) * 3 + 2], nz[j]);
+      atomicAdd(&cstats[0 * C + c], s);
+      atomicAdd(&cstats[1 * C + c], q);
+      atomicAdd(&cstats[2 * C + c], lane_sum(red, m, 2, c));
+      atomic_max_nonneg(&cstats[3 * C + c], lane_max(red, m, 3, c));
+      atomicAdd(&cstats[4 * C + c], lane_sum(red, m, 4, c));
     }
   }
   __syncthreads();
@@ -103,20 +134,11 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restri
   for (int g = threadIdx.x; g < G; g += kThreads) {
     double gs = 0.0, gq = 0.0;
     for (int j = 0; j < D; ++j) {
-      gs += (double)sm[(g * D + j) * 2];
-      gq += (double)sm[(g * D + j) * 2 + 1];
+      gs += (double)chan[(g * D + j) * 2];
+      gq += (double)chan[(g * D + j) * 2 + 1];
     }
     atomicAdd(&sums[((int64_t)n * G + g) * 2], gs);
     atomicAdd(&sums[((int64_t)n * G + g) * 2 + 1], gq);
-  }
-  if (STATS) {
-    for (int c = threadIdx.x; c < C; c += kThreads) {
-      atomicAdd(&cstats[0 * C + c], sm[c * 2]);
-      atomicAdd(&cstats[1 * C + c], sm[c * 2 + 1]);
-      atomicAdd(&cstats[2 * C + c], sm[2 * C + c * 3]);
-      atomic_max_nonneg(&cstats[3 * C + c], sm[2 * C + c * 3 + 1]);
-      atomicAdd(&cstats[4 * C + c], sm[2 * C + c * 3 + 2]);
-    }
   }
 }
 
@@ -126,13 +148,9 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const bf16* __restri
                                                             const void* __restrict__ gamma, const void* __restrict__ beta,
                                                             int pdt, bf16* __restrict__ out, float* __restrict__ cstats,
                                                             float near_zero, float eps, int act, int HW, int C, int G) {
-  extern __shared__ float sm[];  // [C][5] when STATS
+  extern __shared__ float sm[];  // [5][8][PL][V] when STATS
   const int n = blockIdx.y;
   Map m = make_map(C, HW);
-  if (STATS) {
-    for (int i = threadIdx.x; i < C * 5; i += kThreads) sm[i] = 0.f;
-    __syncthreads();
-  }
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
@@ -178,22 +196,17 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const bf16* __restri
     }
   }
   if (STATS) {
+    float acc[5][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int c = m.c0 + j;
-      atomicAdd(&sm[c * 5 + 0], s[j]);
-      atomicAdd(&sm[c * 5 + 1], q[j]);
-      atomicAdd(&sm[c * 5 + 2], sa[j]);
-      atomic_max_nonneg(&sm[c * 5 + 3], mx[j]);
-      atomicAdd(&sm[c * 5 + 4], nz[j]);
-    }
+    for (int j = 0; j < 8; ++j) { acc[0][j] = s[j]; acc[1][j] = q[j]; acc[2][j] = sa[j]; acc[3][j] = mx[j]; acc[4][j] = nz[j]; }
+    deposit<5>(sm, m, acc);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kThreads) {
-      atomicAdd(&cstats[0 * C + c], sm[c * 5 + 0]);
-      atomicAdd(&cstats[1 * C + c], sm[c * 5 + 1]);
-      atomicAdd(&cstats[2 * C + c], sm[c * 5 + 2]);
-      atomic_max_nonneg(&cstats[3 * C + c], sm[c * 5 + 3]);
-      atomicAdd(&cstats[4 * C + c], sm[c * 5 + 4]);
+      atomicAdd(&cstats[0 * C + c], lane_sum(sm, m, 0, c));
+      atomicAdd(&cstats[1 * C + c], lane_sum(sm, m, 1, c));
+      atomicAdd(&cstats[2 * C + c], lane_sum(sm, m, 2, c));
+      atomic_max_nonneg(&cstats[3 * C + c], lane_max(sm, m, 3, c));
+      atomicAdd(&cstats[4 * C + c], lane_sum(sm, m, 4, c));
     }
   }
 }
@@ -205,11 +218,9 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const bf16* __r
                                                                  const void* __restrict__ beta, int pdt,
                                                                  float* __restrict__ dsdb, float eps, int act, int HW,
                                                                  int C, int G) {
-  extern __shared__ float sm[];  // [C][2]
+  extern __shared__ float sm[];  // [2][8][PL][V]
   const int n = blockIdx.y;
   Map m = make_map(C, HW);
-  for (int i = threadIdx.x; i < C * 2; i += kThreads) sm[i] = 0.f;
-  __syncthreads();
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
@@ -248,17 +259,20 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const bf16* __r
       }
     }
   }
+  float acc[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[(m.c0 + j) * 2], ds[j]);
-    atomicAdd(&sm[(m.c0 + j) * 2 + 1], db[j]);
-  }
+  for (int j = 0; j < 8; ++j) { acc[0][j] = ds[j]; acc[1][j] = db[j]; }
+  deposit<2>(sm, m, acc);
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 2; i += kThreads) atomicAdd(&dsdb[(int64_t)n * C * 2 + i], sm[i]);
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    atomicAdd(&dsdb[((int64_t)n * C + c) * 2], lane_sum(sm, m, 0, c));
+    atomicAdd(&dsdb[((int64_t)n * C + c) * 2 + 1], lane_sum(sm, m, 1, c));
+  }
 }
 
 // ---------------------------------------------------------------- backward pass 2: dx
-__global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
+template <bool HAS_RES>
+__global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
                                                                 const double* __restrict__ sums,
                                                                 const void* __restrict__ gamma,
                                                                 const void* __restrict__ beta, int pdt,
@@ -266,13 +280,10 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __re
                                                                 const bf16* __restrict__ dres,
                                                                 float* __restrict__ colsum, float eps, int act, int HW,
                                                                 int C, int G) {
-  extern __shared__ float sm[];  // [C] when colsum
+  extern __shared__ float sm[];  // [1][8][PL][V] when colsum
+  constexpr int kU = 2;          // fewer pixels in flight than the other passes: three streams per pixel
   const int n = blockIdx.y;
   Map m = make_map(C, HW);
-  if (colsum) {
-    for (int i = threadIdx.x; i < C; i += kThreads) sm[i] = 0.f;
-    __syncthreads();
-  }
   float cs[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) cs[j] = 0.f;
@@ -307,31 +318,31 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __re
     c3[j] = pc3;
   }
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
-    bf16x8 vx[kUnroll], vg[kUnroll], vr[kUnroll];
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kU * m.PL) {
+    bf16x8 vx[kU], vg[kU], vr[kU];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const int64_t p = p0 + (int64_t)u * m.PL;
       if (p < m.p_end) {
         vx[u] = ld8(x + base + p * C);
         vg[u] = ld8(dout + base + p * C);
-        if (dres) vr[u] = ld8(dres + base + p * C);
+        if (HAS_RES) vr[u] = ld8(dres + base + p * C);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const int64_t p = p0 + (int64_t)u * m.PL;
       if (p >= m.p_end) break;
       float f[8], g[8], r[8];
       unpack8(vx[u], f);
       unpack8(vg[u], g);
-      if (dres) unpack8(vr[u], r);
+      if (HAS_RES) unpack8(vr[u], r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float gg = g[j];
         if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
         float d = fmaf(a[j], gg, fmaf(c2[j], f[j], c3[j]));
-        if (dres) d += r[j];
+        if (HAS_RES) d += r[j];
         g[j] = d;
         cs[j] += d;
       }
@@ -339,10 +350,12 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_apply_kernel(const bf16* __re
     }
   }
   if (colsum) {
+    float acc[1][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sm[m.c0 + j], cs[j]);
+    for (int j = 0; j < 8; ++j) acc[0][j] = cs[j];
+    deposit<1>(sm, m, acc);
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += kThreads) atomicAdd(&colsum[i], sm[i]);
+    for (int c = threadIdx.x; c < C; c += kThreads) atomicAdd(&colsum[c], lane_sum(sm, m, 0, c));
   }
 }
 
@@ -392,10 +405,10 @@ extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, f
   cudaStream_t st = as_stream(stream);
   VCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * G, st));
   if (chan_stats_in)
-    gn_stats_kernel<true><<<gn_grid(N, HW, C), kThreads, C * 5 * sizeof(float), st>>>((const bf16*)x, sums, chan_stats_in,
+    gn_stats_kernel<true><<<gn_grid(N, HW, C), kThreads, (5 * 8 * kThreads + 2 * C) * sizeof(float), st>>>((const bf16*)x, sums, chan_stats_in,
                                                                                      near_zero, HW, C, G);
   else
-    gn_stats_kernel<false><<<gn_grid(N, HW, C), kThreads, C * 2 * sizeof(float), st>>>((const bf16*)x, sums, nullptr,
+    gn_stats_kernel<false><<<gn_grid(N, HW, C), kThreads, (2 * 8 * kThreads + 2 * C) * sizeof(float), st>>>((const bf16*)x, sums, nullptr,
                                                                                       near_zero, HW, C, G);
   VCD_LAUNCH_CHECK();
   return 0;
@@ -407,7 +420,7 @@ extern "C" int vcd_gn_apply_fwd(const void* x, const double* sums, const void* g
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
   if (chan_stats_out)
-    gn_apply_kernel<true><<<gn_grid(N, HW, C), kThreads, C * 5 * sizeof(float), st>>>(
+    gn_apply_kernel<true><<<gn_grid(N, HW, C), kThreads, 5 * 8 * kThreads * sizeof(float), st>>>(
         (const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, chan_stats_out, near_zero, eps, act_silu, HW, C, G);
   else
     gn_apply_kernel<false><<<gn_grid(N, HW, C), kThreads, 0, st>>>((const bf16*)x, sums, gamma, beta, param_dtype,
@@ -422,7 +435,7 @@ extern "C" int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* 
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
   VCD_CUDA(cudaMemsetAsync(dsdb, 0, sizeof(float) * 2 * N * C, st));
-  gn_bwd_reduce_kernel<<<gn_grid(N, HW, C), kThreads, C * 2 * sizeof(float), st>>>(
+  gn_bwd_reduce_kernel<<<gn_grid(N, HW, C), kThreads, 2 * 8 * kThreads * sizeof(float), st>>>(
       (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, eps, act_silu, HW, C, G);
   VCD_LAUNCH_CHECK();
   return 0;
@@ -433,9 +446,15 @@ extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* s
                                 float eps, int act_silu, int N, int HW, int C, int G, vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
   if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, as_stream(stream)));
-  gn_bwd_apply_kernel<<<gn_grid(N, HW, C), kThreads, dx_colsum ? C * sizeof(float) : 0, as_stream(stream)>>>(
-      (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum,
-      eps, act_silu, HW, C, G);
+  const size_t smem = dx_colsum ? 8 * kThreads * sizeof(float) : 0;
+  if (dres)
+    gn_bwd_apply_kernel<true><<<gn_grid(N, HW, C), kThreads, smem, as_stream(stream)>>>(
+        (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum,
+        eps, act_silu, HW, C, G);
+  else
+    gn_bwd_apply_kernel<false><<<gn_grid(N, HW, C), kThreads, smem, as_stream(stream)>>>(
+        (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, nullptr, dx_colsum, eps,
+        act_silu, HW, C, G);
   VCD_LAUNCH_CHECK();
   return 0;
 }

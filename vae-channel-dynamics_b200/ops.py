@@ -114,19 +114,26 @@ class PackedWeights:
 
     def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
         key = (weight.data_ptr(), weight._version, weight.dtype, None if bias is None else (bias.data_ptr(), bias._version))
-        if key != self.key:
+        # under CUDA-graph capture the pack kernel must be part of the graph: every replay sees updated weights
+        if key != self.key or torch.cuda.is_current_stream_capturing():
             _require_cuda(weight, "conv weight")
             w = weight.detach()
             if not w.is_contiguous():
                 w = w.contiguous()
             cout, cin = w.shape[0], w.shape[1]
             kh, kw = (w.shape[2], w.shape[3]) if w.dim() == 4 else (1, 1)
-            self.wf = torch.empty(kh * kw * cout * cin, dtype=torch.bfloat16, device=w.device)
-            self.wd = torch.empty(kh * kw * cout * cin, dtype=torch.bfloat16, device=w.device)
-            self.bias = None if bias is None else torch.empty(cout, dtype=torch.float32, device=w.device)
+            n = kh * kw * cout * cin
+            if self.wf is None or self.wf.numel() != n or self.wf.device != w.device:
+                self.wf = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+                self.wd = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+                self.bias = None if bias is None else torch.empty(cout, dtype=torch.float32, device=w.device)
             call("vcd_pack_conv_weight", _p(w), _p(None if bias is None else bias.detach()), dtype_code(w), cout, cin,
                  kh, kw, _p(self.wf), _p(self.wd), _p(self.bias), _st())
             self.key = key
+        return self.wf, self.wd, self.bias
+
+    def current(self):
+        """the packs of the forward pass (backward never repacks)"""
         return self.wf, self.wd, self.bias
 
 
@@ -192,7 +199,7 @@ class _ConvFn(torch.autograd.Function):
         xs, weight, bias = ctx.saved_tensors
         N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl = ctx.cfg
         dy = _nhwc(dy)
-        wf, wd, _ = ctx.packs.get(weight, bias)
+        wf, wd, _ = ctx.packs.current()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             if planes:

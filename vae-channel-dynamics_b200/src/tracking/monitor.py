@@ -231,6 +231,9 @@ class ActivityMonitor:
         extended: Dict[str, Dict[str, Any]] = {}
         gathered = self._gather()
         order = [i for i in self._fired if i in self._targets]
+        # forwards replayed from a CUDA graph do not run the Python callback: append the remaining subscribed
+        # targets in registration order (their device accumulators say whether they fired)
+        order += [i for i in self._targets if i not in order]
         for ident in order:
             tgt = self._targets[ident]
             entry: Dict[str, Any] = {}
