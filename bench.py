@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--track-interval", type=int, default=20)
-    ap.add_argument("--eager", action="store_true", help="no CUDA graph: the per-op path unchanged train.py gets (DDP for N>1)")
+    ap.add_argument("--graph", action="store_true", help="replay forward+loss+backward from one CUDA graph (GraphedVAEStep); "
+                    "default is the eager per-op path that unchanged train.py gets (DDP for N>1)")
     ap.add_argument("--quick", action="store_true", help="profiling aid: warm-up as given, no e2e/roofline/cpu legs")
     return ap.parse_args()
 
@@ -315,7 +316,7 @@ def main():
     wrapper = SDXLVAEWrapper("random-init:42", torch_dtype=torch.bfloat16).to(dev)
     plant_dead_channels(wrapper.vae, torch)
     model = wrapper
-    if world > 1 and args.eager:
+    if world > 1 and not args.graph:
         model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[local_rank], gradient_as_bucket_view=True)
     opt = torch.optim.AdamW(wrapper.parameters(), lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8, fused=True)
     tcfg = {"enabled": True, "track_interval": args.track_interval,
@@ -337,7 +338,7 @@ def main():
     launches_per_step = [0]
 
     graphed = None
-    if not args.eager:   # forward + loss + backward captured once in a CUDA graph (vcd_b200.GraphedVAEStep)
+    if args.graph:   # forward + loss + backward captured once in a CUDA graph (vcd_b200.GraphedVAEStep)
         graphed = vcd_b200.GraphedVAEStep(wrapper, kl_weight, resident[0])
 
     def train_step(x):
@@ -425,7 +426,7 @@ def main():
                                    f"classify+nudge every {args.track_interval} steps, random-init SDXL-VAE seed 42, bf16 weights",
                        "resolution": R, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "optimizer": "clip_grad_norm 1.0 + AdamW (torch fused) as in train.py:301-304",
-                       "execution": "eager per-op launches" if args.eager else "forward+loss+backward replayed from one CUDA graph (GraphedVAEStep); clip/AdamW/tracker eager",
+                       "execution": "eager per-op launches (DDP bucketed all-reduce for N>1)" if not args.graph else "forward+loss+backward replayed from one CUDA graph (GraphedVAEStep); clip/AdamW/tracker eager",
                        "l2": "4 distinct input batches rotated; every activation tensor exceeds the 126 MB L2 at this size",
                        "train_tflop_per_image": fl_img / 1e12,
                        "step_mfu_of_sustained_peak": (value / world) * fl_img / 1e12 / peak_t,

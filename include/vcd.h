@@ -76,6 +76,21 @@ int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, const fl
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
                      int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream);
 
+/* ---- Upsample2D fused: nearest x2 + conv3x3(pad 1) as four 2x2 phase convolutions on the low-resolution
+ * tensor with pre-summed weights ([upstream] Upsample2D in decoder.up_blocks.{0,1,2}.upsamplers.0).
+ * 16 tap products per low-res pixel instead of 36; the upsampled tensor is never materialised.
+ *   wf16: bf16 [16][Cout][Cin], wd16: bf16 [16][Cin][Cout]  (index ((a*2+b)*2+dh)*2+dw)
+ *   x [N][H][W][Cin] -> y [N][2H][2W][Cout];  dy_planes = vcd_space_to_planes(dy) = [N][2][2][H][W][Cout] */
+int vcd_pack_upconv_weight(const void* w, const void* bias, int dtype, int Cout, int Cin, void* wf16, void* wd16,
+                           float* bias_f32, vcd_stream_t stream);
+int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* bias, void* y, int N, int H, int W, int Cin,
+                       int Cout, vcd_stream_t stream);
+int vcd_upconv2d_dgrad(const void* dy_planes, const void* wd16, void* dx, int N, int H, int W, int Cin, int Cout,
+                       vcd_stream_t stream);
+int64_t vcd_upconv2d_wgrad_ws_bytes(int Cin, int Cout);
+int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw, void* db, const float* db_colsum, int dtype,
+                       void* ws, int N, int H, int W, int Cin, int Cout, vcd_stream_t stream);
+
 /* NHWC [N][H][W][C] <-> parity planes [N][2][2][H/2][W/2][C] (stride-2 convs), H and W even */
 int vcd_space_to_planes(const void* x, void* xp, int N, int H, int W, int C, vcd_stream_t stream);
 int vcd_planes_to_space(const void* xp, void* x, int N, int H, int W, int C, vcd_stream_t stream);

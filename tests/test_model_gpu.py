@@ -220,21 +220,31 @@ def test_tracked_training_step_with_classify_and_nudge(vcd, pair):
     assert w.vae.encoder.down_blocks[0].resnets[0].norm1._track_out is None
 
 
-def test_graphed_step_matches_eager_step(vcd, pair):
+def test_graphed_step_matches_eager_step(vcd, pair, monkeypatch):
     """GraphedVAEStep (forward+loss+backward replayed from a CUDA graph) against the eager per-op path: same
     losses up to the reparameterisation noise, gradients aligned, weight packs refreshed inside the graph."""
     oracle, _ = pair
     vcd.add_src_to_path()
     from models.sdxl_vae_wrapper import SDXLVAEWrapper
-    w = SDXLVAEWrapper("random-init:42", torch_dtype=torch.bfloat16).cuda()
-    w.vae.load_state_dict(oracle.state_dict())
     torch.manual_seed(11)
     x = torch.rand(2, 3, 64, 64, device="cuda") * 2 - 1
-    out = w(x, sample_posterior=True)
+    # eager reference on its own wrapper (AccumulateGrad nodes created on the default stream must not be
+    # reused inside a capture)
+    # the same reparameterisation noise in both runs (random-init latents are noise-dominated): torch.randn of the
+    # latent shape returns a copy of one fixed tensor, eagerly and inside the captured graph
+    noise = torch.randn(2, 4, 8, 8, device="cuda")
+    real_randn = torch.randn
+    monkeypatch.setattr(torch, "randn", lambda *a, **k: noise.clone() if tuple(a[0] if len(a) == 1 else a) == tuple(noise.shape)
+                        else real_randn(*a, **k))
+    we = SDXLVAEWrapper("random-init:42", torch_dtype=torch.bfloat16).cuda()
+    we.vae.load_state_dict(oracle.state_dict())
+    out = we(x, sample_posterior=True)
     total, rec, kl = vcd.vae_loss(out, x, 1e-6)
     total.backward()
-    eager = {n: p.grad.detach().float().clone() for n, p in w.named_parameters()}
-    w.zero_grad(set_to_none=True)
+    eager = {n: p.grad.detach().float().clone() for n, p in we.named_parameters()}
+    del we, out, total
+    w = SDXLVAEWrapper("random-init:42", torch_dtype=torch.bfloat16).cuda()
+    w.vae.load_state_dict(oracle.state_dict())
     g = vcd.GraphedVAEStep(w, 1e-6, x)
     t2, r2, k2 = g.step(x)
     assert g.launches_per_replay > 300

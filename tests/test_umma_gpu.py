@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 from test_kernels_gpu import _conv_case
-from util import bf16_round, rel_err
+from util import bf16_round, nchw, nhwc, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-2
@@ -94,3 +94,28 @@ def test_attention_core(vcd, T):
     o.backward(g.to(torch.bfloat16))
     for a, b in ((qp, qr), (kp, kr), (vp, vr)):
         assert rel_err(a.grad, b.grad) < 3e-2
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout", [(2, 8, 8, 128, 128), (1, 16, 16, 256, 256), (3, 8, 8, 512, 512),
+                                            (2, 12, 20, 128, 256), (1, 6, 72, 256, 128)])
+def test_upconv_fused_matches_torch(vcd, N, H, W, cin, cout):
+    """Upsample2D (nearest x2 + conv3x3 pad 1) as four phase convolutions on the low-resolution tensor
+    (vcd_upconv2d_*) against F.interpolate + F.conv2d in fp32 on the same bf16-rounded inputs: output,
+    input gradient, weight and bias gradients."""
+    ops = vcd.ops
+    x = bf16_round(torch.randn(N, cin, H, W, device="cuda"))
+    w = bf16_round(torch.randn(cout, cin, 3, 3, device="cuda") / math.sqrt(9 * cin))
+    b = torch.randn(cout, device="cuda")
+    g = bf16_round(torch.randn(N, cout, 2 * H, 2 * W, device="cuda"))
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    ref = F.conv2d(F.interpolate(xr, scale_factor=2.0, mode="nearest"), wr, br, padding=1)
+    ref.backward(g)
+    xp = nhwc(x).requires_grad_()
+    wp, bp = w.clone().requires_grad_(), b.clone().requires_grad_()
+    y = ops.upconv2d(xp, wp, bp, ops.UpconvPackedWeights())
+    assert y.shape == (N, 2 * H, 2 * W, cout)
+    assert rel_err(nchw(y), ref) < TOL
+    y.backward(nhwc(g))
+    assert rel_err(nchw(xp.grad), xr.grad) < TOL
+    assert rel_err(wp.grad, wr.grad) < TOL
+    assert rel_err(bp.grad, br.grad) < TOL

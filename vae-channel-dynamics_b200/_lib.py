@@ -25,6 +25,11 @@ SIGNATURES = {
     "vcd_conv2d_dgrad": (_i, [_p] * 5 + [_i] * 14 + [_p]),
     "vcd_conv2d_wgrad_ws_bytes": (_i64, [_i] * 8),
     "vcd_conv2d_wgrad": (_i, [_p] * 5 + [_i] + [_p] + [_i] * 14 + [_p]),
+    "vcd_pack_upconv_weight": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "vcd_upconv2d_fprop": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vcd_upconv2d_dgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vcd_upconv2d_wgrad_ws_bytes": (_i64, [_i, _i]),
+    "vcd_upconv2d_wgrad": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     "vcd_space_to_planes": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vcd_planes_to_space": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vcd_upsample2x_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -404,12 +404,188 @@ int narrow_conv(const void* in, const void* pack, const float* bias, void* out, 
   return umma_launch(mA, mB, p, 128, st);
 }
 
+__global__ void convert_f32_from_param_kernel(const void* __restrict__ b, int dt, int n, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = load_param(b, dt, i);
+}
+
 __global__ void convert_f32_kernel(const float* __restrict__ in, void* __restrict__ out, int dt, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     store_param(out, dt, i, in[i]);
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------- Upsample2D (nearest x2) + 3x3 conv, fused
+// [upstream] F.interpolate(x, 2, "nearest") followed by conv3x3(pad 1) equals four 2x2 convolutions on the
+// LOW-resolution tensor, one per output parity (a, b), with pre-summed weights:
+//   y[2h+a, 2w+b] = sum_{dh,dw in {0,1}} x[h + dh-1+a, w + dw-1+b] * Wsum[a][b][dh][dw]
+//   Wsum[a][b][dh][dw] = sum_{kh in R(a,dh)} sum_{kw in R(b,dw)} W[kh][kw],  R(0,0)={0} R(0,1)={1,2} R(1,0)={0,1} R(1,1)={2}
+// 16 tap-products per low-res pixel instead of 36: 2.25x fewer FLOPs, and the upsampled tensor never exists.
+namespace {
+__device__ __forceinline__ int up_group(int a, int k) { return a == 0 ? (k == 0 ? 0 : 1) : (k <= 1 ? 0 : 1); }
+
+__global__ void pack_upconv_kernel(const void* __restrict__ w, int dt, int Cout, int Cin, bf16* __restrict__ wf,
+                                   bf16* __restrict__ wd) {
+  const int64_t total = (int64_t)16 * Cout * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    int64_t r = i / Cin;
+    const int co = (int)(r % Cout);
+    const int q = (int)(r / Cout);
+    const int dw = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
+    float acc = 0.f;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        if (up_group(a, kh) == dh && up_group(b, kw) == dw) acc += load_param(w, dt, (((int64_t)co * Cin + ci) * 3 + kh) * 3 + kw);
+    const bf16 v = __float2bfloat16_rn(acc);
+    wf[i] = v;
+    wd[((int64_t)q * Cin + ci) * Cout + co] = v;
+  }
+}
+// acc16 fp32 [16][Cout][Cin] -> ws [9][Cout][Cin]: dW[kh][kw] = sum_{a,b} acc16[a][b][group(a,kh)][group(b,kw)]
+__global__ void upconv_wgrad_combine_kernel(const float* __restrict__ acc16, float* __restrict__ ws, int Cout, int Cin) {
+  const int64_t per = (int64_t)Cout * Cin, total = 9 * per;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i / per);
+    const int64_t e = i % per;
+    const int kh = t / 3, kw = t % 3;
+    float v = 0.f;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) v += acc16[(int64_t)(((a * 2 + b) * 2 + up_group(a, kh)) * 2 + up_group(b, kw)) * per + e];
+    ws[i] = v;
+  }
+}
+}  // namespace
+
+extern "C" int vcd_pack_upconv_weight(const void* w, const void* bias, int dtype, int Cout, int Cin, void* wf16,
+                                      void* wd16, float* bias_f32, vcd_stream_t stream) {
+  VCD_CHECK_ARG(w && wf16 && wd16, "pack_upconv_weight: null pointer");
+  cudaStream_t st = as_stream(stream);
+  pack_upconv_kernel<<<ew_blocks((int64_t)16 * Cout * Cin), 256, 0, st>>>(w, dtype, Cout, Cin, (bf16*)wf16, (bf16*)wd16);
+  VCD_LAUNCH_CHECK();
+  if (bias && bias_f32) {
+    convert_f32_from_param_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(bias, dtype, Cout, bias_f32);
+    VCD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// x [N][H][W][Cin] -> y [N][2H][2W][Cout]
+extern "C" int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* bias, void* y, int N, int H, int W,
+                                  int Cin, int Cout, vcd_stream_t stream) {
+  VCD_CHECK_ARG(x && wf16 && y, "upconv fprop: null pointer");
+  VCD_CHECK_ARG(Cin % 128 == 0 && Cout % 128 == 0, "upconv: channels must be multiples of 128 (Cin=%d Cout=%d)", Cin, Cout);
+  const int bn = pick_block_n(Cout);
+  CUtensorMap mA, mB;
+  int rc;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      UmmaParams p;
+      memset(&p, 0, sizeof(p));
+      p.form = 0;
+      choose_tile(128, W, H, N, p);
+      p.ntaps = 4;
+      for (int dh = 0; dh < 2; ++dh)
+        for (int dw = 0; dw < 2; ++dw) {
+          const int t = dh * 2 + dw;
+          p.tap_dh[t] = dh - 1 + a; p.tap_dw[t] = dw - 1 + b; p.tap_plane[t] = 0;
+          p.tap_brow[t] = (((a * 2 + b) * 2 + dh) * 2 + dw) * Cout;
+        }
+      p.n_tiles = Cout / bn; p.kc_per_tap = Cin / 64;
+      p.out = (bf16*)y + ((long long)a * 2 * W + b) * Cout; p.bias = bias; p.alpha = 1.f;
+      p.out_sn = 4ll * H * W * Cout; p.out_sh = 4ll * W * Cout; p.out_sw = 2ll * Cout;
+      p.Nout = Cout;
+      set_form0_desc(p, bn);
+      p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+      if ((rc = make_act_map(&mA, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+      if ((rc = make_act_map(&mB, wf16, Cin, 16 * Cout, 1, 1, 1, 64, bn, 1, 1))) return rc;
+      if ((rc = umma_launch(mA, mB, p, bn, as_stream(stream)))) return rc;
+    }
+  return 0;
+}
+
+// dy_planes [N][2][2][H][W][Cout] (vcd_space_to_planes of dy [N][2H][2W][Cout]) -> dx [N][H][W][Cin]
+extern "C" int vcd_upconv2d_dgrad(const void* dy_planes, const void* wd16, void* dx, int N, int H, int W, int Cin,
+                                  int Cout, vcd_stream_t stream) {
+  VCD_CHECK_ARG(dy_planes && wd16 && dx, "upconv dgrad: null pointer");
+  VCD_CHECK_ARG(Cin % 128 == 0 && Cout % 128 == 0, "upconv: channels must be multiples of 128");
+  const int bn = pick_block_n(Cin);
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.form = 0;
+  choose_tile(128, W, H, N, p);
+  p.ntaps = 16;
+  for (int q = 0; q < 16; ++q) {
+    const int dw = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
+    p.tap_dh[q] = -(dh - 1 + a); p.tap_dw[q] = -(dw - 1 + b); p.tap_plane[q] = a * 2 + b;
+    p.tap_brow[q] = q * Cin;
+  }
+  p.n_tiles = Cin / bn; p.kc_per_tap = Cout / 64;
+  p.out = (bf16*)dx; p.alpha = 1.f;
+  p.out_sn = (long long)H * W * Cin; p.out_sh = (long long)W * Cin; p.out_sw = Cin;
+  p.Nout = Cin;
+  set_form0_desc(p, bn);
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  CUtensorMap mA, mB;
+  int rc;
+  if ((rc = make_act_map(&mA, dy_planes, Cout, W, H, 4, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+  if ((rc = make_act_map(&mB, wd16, Cout, 16 * Cin, 1, 1, 1, 64, bn, 1, 1))) return rc;
+  return umma_launch(mA, mB, p, bn, as_stream(stream));
+}
+
+extern "C" int64_t vcd_upconv2d_wgrad_ws_bytes(int Cin, int Cout) {
+  return align256(((int64_t)9 * Cout * Cin + Cout) * 4) + align256((int64_t)16 * Cout * Cin * 4);
+}
+
+extern "C" int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw, void* db, const float* db_colsum,
+                                  int dtype, void* ws, int N, int H, int W, int Cin, int Cout, vcd_stream_t stream) {
+  VCD_CHECK_ARG(x && dy_planes && dw && ws, "upconv wgrad: null pointer");
+  VCD_CHECK_ARG(Cin % 128 == 0 && Cout % 128 == 0, "upconv: channels must be multiples of 128");
+  cudaStream_t st = as_stream(stream);
+  const int64_t main_elems = (int64_t)9 * Cout * Cin;
+  float* wsf = (float*)ws;
+  float* acc16 = (float*)((char*)ws + align256((main_elems + Cout) * 4));
+  VCD_CUDA(cudaMemsetAsync(wsf + main_elems, 0, Cout * sizeof(float), st));
+  VCD_CUDA(cudaMemsetAsync(acc16, 0, (size_t)16 * Cout * Cin * sizeof(float), st));
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.form = 1;
+  choose_tile(64, W, H, N, p);
+  const int bn = pick_block_n(Cin);
+  p.ntaps = 16;
+  for (int q = 0; q < 16; ++q) {
+    const int dw_ = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
+    p.tap_dh[q] = dh - 1 + a; p.tap_dw[q] = dw_ - 1 + b; p.tap_plane[q] = 0;
+    p.tap_plane_a[q] = a * 2 + b;
+  }
+  p.n_tiles = Cin / bn; p.m_tiles = Cout / 128;
+  p.Mout = Cout; p.Nout = Cin;
+  p.acc = acc16;
+  p.batches = 1;
+  p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int base_tiles = p.ntaps * p.m_tiles * p.n_tiles;
+  int splits = pick_splits(base_tiles, p.k_tiles);
+  p.k_per_split = (p.k_tiles + splits - 1) / splits;
+  p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
+  set_form1_desc(p, bn);
+  p.total_tiles = base_tiles * p.splits;
+  CUtensorMap mA, mB;
+  int rc;
+  if ((rc = make_act_map(&mA, dy_planes, Cout, W, H, 4, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+  if ((rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+  if ((rc = umma_launch(mA, mB, p, bn, st))) return rc;
+  upconv_wgrad_combine_kernel<<<ew_blocks(main_elems), 256, 0, st>>>(acc16, wsf, Cout, Cin);
+  VCD_LAUNCH_CHECK();
+  if (db) {
+    if (db_colsum) {
+      VCD_CUDA(cudaMemcpyAsync(wsf + main_elems, db_colsum, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if ((rc = conv_bias_grad(dy_planes, wsf + main_elems, (int64_t)N * 4 * H * W, Cout, st))) {
+      return rc;
+    }
+  }
+  return conv_wgrad_finalize(wsf, dw, db, dtype, Cout, Cin, 9, st);
+}
 
 extern "C" int vcd_conv_umma_supported(int Cin, int Cout, int KH, int KW, int stride) {
   return umma_shape_ok(Cin, Cout, KH, KW, stride) ? 1 : 0;

@@ -207,7 +207,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
 #pragma unroll
           for (int b = 0; b < 2; ++b)
-            tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, pt.w0, pt.h0, 0, pt.n0);
+            tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, pt.w0, pt.h0, p.tap_plane_a[rt.tap], pt.n0);
 #pragma unroll
           for (int b = 0; b < BLOCK_N / 64; ++b)
             tma_load_5d(sa + kStageA + b * 8192, &mapB, full_bar(stage), rt.nt * BLOCK_N + b * 64,

@@ -26,11 +26,12 @@ struct UmmaParams {
   int tiles_w, tiles_h, tiles_n;
   // taps
   int ntaps;
-  int tap_dw[9], tap_dh[9], tap_plane[9];
+  int tap_dw[16], tap_dh[16], tap_plane[16];
+  int tap_plane_a[16];  // form 1: plane of the A (dy) operand per tap (upsample-conv wgrad), else 0
   // form 0
   int n_tiles;       // Nout / BLOCK_N
   int kc_per_tap;    // K / 64
-  int tap_brow[9];   // B row offset per tap
+  int tap_brow[16];  // B row offset per tap
   int b_batch_rows;  // B row offset per image (batched GEMM); 0 = shared weights
   bf16* out;
   const bf16* residual;

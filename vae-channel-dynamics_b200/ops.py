@@ -232,6 +232,85 @@ def conv2d(x, weight, bias, packs, stride=1, pad_t=1, pad_l=1, out_hw=None, resi
                          _conv_impl if impl is None else impl)
 
 
+class UpconvPackedWeights:
+    """bf16 operand packs of an Upsample2D conv in its four-phase form (vcd_pack_upconv_weight):
+    wf [16][Cout][Cin] for fprop, wd [16][Cin][Cout] for dgrad, fp32 bias."""
+
+    def __init__(self):
+        self.key = None
+        self.wf = self.wd = self.bias = None
+
+    def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+        key = (weight.data_ptr(), weight._version, weight.dtype, None if bias is None else (bias.data_ptr(), bias._version))
+        if key != self.key or torch.cuda.is_current_stream_capturing():
+            _require_cuda(weight, "conv weight")
+            w = weight.detach()
+            if not w.is_contiguous():
+                w = w.contiguous()
+            cout, cin = w.shape[0], w.shape[1]
+            n = 16 * cout * cin
+            if self.wf is None or self.wf.numel() != n or self.wf.device != w.device:
+                self.wf = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+                self.wd = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+                self.bias = None if bias is None else torch.empty(cout, dtype=torch.float32, device=w.device)
+            call("vcd_pack_upconv_weight", _p(w), _p(None if bias is None else bias.detach()), dtype_code(w), cout, cin,
+                 _p(self.wf), _p(self.wd), _p(self.bias), _st())
+            self.key = key
+        return self.wf, self.wd, self.bias
+
+    def current(self):
+        return self.wf, self.wd, self.bias
+
+
+def upconv_supported(cin: int, cout: int) -> bool:
+    return cin % 128 == 0 and cout % 128 == 0 and _conv_impl != IMPL_SIMT
+
+
+class _UpConvFn(torch.autograd.Function):
+    """[upstream] Upsample2D: nearest x2 followed by conv3x3(pad 1), computed as four 2x2 phase convolutions on
+    the low-resolution tensor (include/vcd.h vcd_upconv2d_*): the upsampled tensor is never materialised and the
+    GEMMs do 16/36 of the multiply-adds."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, packs: UpconvPackedWeights):
+        x = _nhwc(x)
+        N, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        wf, wd, b32 = packs.get(weight, bias)
+        y = torch.empty((N, 2 * H, 2 * W, Cout), dtype=torch.bfloat16, device=x.device)
+        call("vcd_upconv2d_fprop", _p(x), _p(wf), _p(b32), _p(y), N, H, W, Cin, Cout, _st())
+        ctx.save_for_backward(x, weight, bias)
+        ctx.packs = packs
+        ctx.cfg = (N, H, W, Cin, Cout)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        N, H, W, Cin, Cout = ctx.cfg
+        dy = _nhwc(dy)
+        wf, wd, _ = ctx.packs.current()
+        colsum = pop_colsum(dy) if bias is not None else None
+        dyp = torch.empty((N, 4, H, W, Cout), dtype=torch.bfloat16, device=dy.device)
+        call("vcd_space_to_planes", _p(dy), _p(dyp), N, 2 * H, 2 * W, Cout, _st())
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
+            call("vcd_upconv2d_dgrad", _p(dyp), _p(wd), _p(dx), N, H, W, Cin, Cout, _st())
+        if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+            db = None if bias is None else torch.empty_like(bias)
+            nbytes = _lib.lib().vcd_upconv2d_wgrad_ws_bytes(Cin, Cout)
+            ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
+            call("vcd_upconv2d_wgrad", _p(x), _p(dyp), _p(dw), _p(db), _p(colsum), dtype_code(weight), _p(ws), N, H, W,
+                 Cin, Cout, _st())
+        return dx, dw, db, None
+
+
+def upconv2d(x, weight, bias, packs):
+    return _UpConvFn.apply(x, weight, bias, packs)
+
+
 # ------------------------------------------------------------------------------------------
 # GroupNorm (+SiLU) with fused statistics
 # ------------------------------------------------------------------------------------------

@@ -194,8 +194,14 @@ class Upsample2D(nn.Module):
         super().__init__()
         self.conv = B200Conv2d(c, c, 3, padding=1)
 
+        self._up_packs = ops.UpconvPackedWeights()
+
     def forward(self, x):
-        return self.conv(_logi(ops.upsample2x(_phys(x))))
+        c = self.conv
+        if _hooked(c) or c._track_out is not None or not ops.upconv_supported(c.in_channels, c.out_channels):
+            # a hook on the conv must observe the upsampled tensor: materialise it
+            return c(_logi(ops.upsample2x(_phys(x))))
+        return _logi(ops.upconv2d(_phys(x), c.weight, c.bias, self._up_packs))
 
 
 class DownEncoderBlock2D(nn.Module):
