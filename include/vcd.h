@@ -91,6 +91,10 @@ int64_t vcd_upconv2d_wgrad_ws_bytes(int Cin, int Cout);
 int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw, void* db, const float* db_colsum, int dtype,
                        void* ws, int N, int H, int W, int Cin, int Cout, vcd_stream_t stream);
 
+/* Number of launches of the CTA-pair (tcgen05.mma.cta_group::2, halo-reuse) kernel since the library was loaded:
+ * lets tests and the bench assert that the pair path, not the single-CTA kernel, served a layer. */
+int64_t vcd_pair_kernel_launches(void);
+
 /* NHWC [N][H][W][C] <-> parity planes [N][2][2][H/2][W/2][C] (stride-2 convs), H and W even */
 int vcd_space_to_planes(const void* x, void* xp, int N, int H, int W, int C, vcd_stream_t stream);
 int vcd_planes_to_space(const void* xp, void* x, int N, int H, int W, int C, vcd_stream_t stream);

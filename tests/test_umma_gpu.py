@@ -119,3 +119,55 @@ def test_upconv_fused_matches_torch(vcd, N, H, W, cin, cout):
     assert rel_err(nchw(xp.grad), xr.grad) < TOL
     assert rel_err(wp.grad, wr.grad) < TOL
     assert rel_err(bp.grad, br.grad) < TOL
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,stride", [
+    (2, 16, 16, 128, 128, 3, 1),    # 2 tiles per image, 4 tiles = 2 pairs
+    (3, 16, 8, 512, 512, 3, 1),     # 3 tiles: the last pair has an empty second CTA; 2 n-tiles of 256
+    (1, 40, 20, 128, 256, 3, 1),    # ragged: H, W not multiples of the 16 x 8 tile
+    (2, 32, 32, 256, 128, 3, 1),
+    (1, 64, 64, 128, 128, 3, 1),    # 32 tiles, several items per cluster: pipeline phases wrap
+    (2, 32, 16, 256, 256, 3, 2),    # Downsample2D on parity planes: four halo groups
+    (2, 16, 16, 256, 512, 1, 1),    # 1x1 shortcut as a ROWS-mode GEMM
+    (1, 24, 24, 512, 256, 1, 1),
+])
+def test_conv_pair_kernel(vcd, N, H, W, cin, cout, k, stride):
+    """shapes that must be served by the CTA-pair halo kernel (umma_pair.cu): parity as for test_conv_umma, plus
+    the launch counter proves which kernel ran."""
+    lib = vcd._lib.lib()
+    n0 = lib.vcd_pair_kernel_launches()
+    _conv_case(vcd, N, H, W, cin, cout, k, stride, vcd._lib.IMPL_UMMA)
+    assert lib.vcd_pair_kernel_launches() > n0
+
+
+def test_conv_pair_residual_and_narrow(vcd):
+    lib = vcd._lib.lib()
+    n0 = lib.vcd_pair_kernel_launches()
+    _conv_case(vcd, 2, 32, 32, 256, 256, 3, 1, vcd._lib.IMPL_UMMA, residual=True)
+    assert lib.vcd_pair_kernel_launches() > n0
+    # decoder.conv_out-like: 128 -> 3 channels (narrow N, masked columns) and its dgrad
+    ops = vcd.ops
+    x = bf16_round(torch.randn(2, 128, 32, 32, device="cuda"))
+    w = bf16_round(torch.randn(3, 128, 3, 3, device="cuda") / 34.0)
+    b = torch.randn(3, device="cuda")
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    ref = F.conv2d(xr, wr, b, padding=1)
+    g = bf16_round(torch.randn_like(ref))
+    ref.backward(g)
+    xp = nhwc(x).requires_grad_()
+    wp = w.clone().requires_grad_()
+    n1 = lib.vcd_pair_kernel_launches()
+    y = ops.conv2d(xp, wp, b, ops.PackedWeights())
+    assert lib.vcd_pair_kernel_launches() > n1
+    assert rel_err(nchw(y), ref) < TOL
+    y.backward(nhwc(g))
+    assert rel_err(nchw(xp.grad), xr.grad) < TOL
+    assert rel_err(wp.grad, wr.grad) < TOL
+
+
+def test_upconv_pair_kernel(vcd):
+    lib = vcd._lib.lib()
+    n0 = lib.vcd_pair_kernel_launches()
+    test_upconv_fused_matches_torch(vcd, 2, 32, 16, 256, 256)
+    test_upconv_fused_matches_torch(vcd, 1, 16, 24, 512, 512)
+    assert lib.vcd_pair_kernel_launches() >= n0 + 10   # 4 phase fprops + 1 dgrad per call

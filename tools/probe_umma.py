@@ -1,0 +1,25 @@
+"""Hardware probe: K-major SWIZZLE_128B UMMA descriptors whose start address is shifted by whole 128-byte rows
+inside one TMA-written tile (vcd_debug_umma_shifted).  Prints max error per (row shift, base-offset mode)."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import vcd_b200
+
+lib = vcd_b200._lib.lib()
+fn = lib.vcd_debug_umma_shifted
+fn.restype = C.c_int
+fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+torch.manual_seed(0)
+A = torch.randn(144, 64, device="cuda").to(torch.bfloat16)
+B = torch.randn(64, 64, device="cuda").to(torch.bfloat16)
+for mode in (0, 1):
+    for r0 in range(0, 17):
+        out = torch.zeros(128, 64, device="cuda")
+        rc = fn(A.data_ptr(), B.data_ptr(), out.data_ptr(), r0, mode, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ref = A[r0:r0 + 128].float() @ B.float().t()
+        err = float((out - ref).abs().max())
+        print(f"mode {mode} r0 {r0:2d} rc {rc} max|err| {err:.4f}  {'OK' if err < 0.05 else 'MISMATCH'}")

@@ -5,6 +5,7 @@
 
 #include "conv_dispatch.h"
 #include "umma_gemm.cuh"
+#include "umma_pair.cuh"
 
 // ---------------------------------------------------------------- error / device info (C ABI)
 static thread_local char g_err[512] = "";
@@ -77,6 +78,59 @@ int pick_splits(int base_tiles, int k_tiles) {
   return splits < 1 ? 1 : splits;
 }
 
+// ---------------------------------------------------------------- CTA-pair kernel (umma_pair.cu) front end
+// BLOCK_N for the pair kernel: 256 when Nout allows it, unless 128 fills the last wave of 74 clusters visibly better
+int pair_block_n(int pairs, int Nout) {
+  // N = 128 tiles are bound by the shared-memory operand bandwidth (A 4 KB + B 2 KB per 64-cycle MMA), so the wider
+  // tile wins whenever the channel count allows it, even with a ragged last wave
+  (void)pairs;
+  return (Nout % 256 != 0) ? 128 : 256;
+}
+// implicit-GEMM convolution with halo reuse: returns 1 when launched, 0 when the shape is not eligible, < 0 on error
+int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, int Ht, const PairTap* taps, int ntaps,
+                  const void* wpack, int wrows, const float* bias, const void* residual, void* out, long long sn,
+                  long long sh, long long sw, int Nout, cudaStream_t st) {
+  if (!pair_enabled() || C % 64 != 0) return 0;
+  PairParams p;
+  memset(&p, 0, sizeof(p));
+  int box_h = 0;
+  if (!pair_setup_halo(p, Wt, Ht, N, taps, ntaps, 128, &box_h)) return 0;
+  const int bn = pair_block_n(p.pairs, Nout);
+  pair_setup_halo(p, Wt, Ht, N, taps, ntaps, bn, &box_h);
+  p.n_tiles = (Nout + bn - 1) / bn;
+  p.kc = C / 64;
+  p.out = (bf16*)out; p.residual = (const bf16*)residual; p.bias = bias; p.alpha = 1.f;
+  p.out_sn = sn; p.out_sh = sh; p.out_sw = sw;
+  p.Nout = Nout;
+  CUtensorMap mA, mB;
+  int rc;
+  if ((rc = make_act_map(&mA, act, C, Wa, Ha, P, N, 64, p.box_w, box_h, 1))) return rc;
+  if ((rc = make_act_map(&mB, wpack, C, wrows, 1, 1, 1, 64, bn / 2, 1, 1))) return rc;
+  if ((rc = pair_launch(mA, mB, p, bn, st))) return rc;
+  return 1;
+}
+// plain GEMM rows x Nout (1x1 convolutions, Linear, attention products): D[b][m][n] = alpha * A[b][m][:] . B[(b)][n][:]
+int pair_rows_gemm(const void* A, const void* B, const float* bias, const void* residual, void* D, int batch, int M, int Nn,
+                   int K, int b_batched, float alpha, cudaStream_t st) {
+  PairParams p;
+  memset(&p, 0, sizeof(p));
+  const int tiles = (M + 127) / 128;
+  const int pairs = b_batched ? ((tiles + 1) / 2) * batch : (tiles * batch + 1) / 2;
+  const int bn = pair_block_n(pairs, Nn);
+  pair_setup_rows(p, M, batch, b_batched ? 1 : 0, 0, bn);
+  p.n_tiles = (Nn + bn - 1) / bn;
+  p.kc = K / 64;
+  p.b_batch_rows = b_batched ? Nn : 0;
+  p.out = (bf16*)D; p.residual = (const bf16*)residual; p.bias = bias; p.alpha = alpha;
+  p.out_sn = (long long)M * Nn; p.out_sh = 0; p.out_sw = Nn;
+  p.Nout = Nn;
+  CUtensorMap mA, mB;
+  int rc;
+  if ((rc = make_act_map(&mA, A, K, M, 1, 1, batch, 64, 128, 1, 1))) return rc;
+  if ((rc = make_act_map(&mB, B, K, b_batched ? batch * Nn : Nn, 1, 1, 1, 64, bn / 2, 1, 1))) return rc;
+  return pair_launch(mA, mB, p, bn, st);
+}
+
 // taps of a conv seen from the OUTPUT pixel grid, reading the (possibly parity-plane) input
 void fill_fprop_taps(UmmaParams& p, int KH, int KW, int stride, int pad_t, int pad_l, int rows_per_tap) {
   p.ntaps = KH * KW;
@@ -112,6 +166,20 @@ int umma_fprop(const void* x, const void* wf, const float* bias, const void* res
   choose_tile(128, Wo, Ho, N, p);
   const int bn = pick_block_n(Cout);
   fill_fprop_taps(p, KH, KW, stride, pad_t, pad_l, Cout);
+  if (pair_enabled()) {
+    int rc;
+    if (KH * KW == 1 && stride == 1) {  // 1x1 shortcut: a plain GEMM over all pixels
+      VCD_CHECK_ARG((long long)N * H * W < (1ll << 31), "1x1 conv: too many pixels");
+      return pair_rows_gemm(x, wf, bias, residual, y, 1, N * H * W, Cout, Cin, 0, 1.f, st);
+    }
+    PairTap taps[16];
+    for (int t = 0; t < p.ntaps; ++t) taps[t] = PairTap{p.tap_plane[t], p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
+    rc = stride == 1 ? try_pair_halo(x, Cin, W, H, 1, N, Wo, Ho, taps, p.ntaps, wf, KH * KW * Cout, bias, residual, y,
+                                     (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st)
+                     : try_pair_halo(x, Cin, W / 2, H / 2, 4, N, Wo, Ho, taps, p.ntaps, wf, KH * KW * Cout, bias, residual,
+                                     y, (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st);
+    if (rc != 0) return rc < 0 ? rc : 0;
+  }
   p.n_tiles = Cout / bn;
   p.kc_per_tap = Cin / 64;
   p.b_batch_rows = 0;
@@ -148,6 +216,17 @@ int umma_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, in
         p.tap_dh[t] = pad_t - kh; p.tap_dw[t] = pad_l - kw; p.tap_plane[t] = 0;
         p.tap_brow[t] = t * Cin;
       }
+    if (pair_enabled()) {
+      if (KH * KW == 1) {
+        VCD_CHECK_ARG((long long)N * H * W < (1ll << 31), "1x1 conv: too many pixels");
+        return pair_rows_gemm(dy, wd, nullptr, nullptr, dx, 1, N * H * W, Cin, Cout, 0, 1.f, st);
+      }
+      PairTap taps[16];
+      for (int t = 0; t < p.ntaps; ++t) taps[t] = PairTap{0, p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
+      rc = try_pair_halo(dy, Cout, Wo, Ho, 1, N, W, H, taps, p.ntaps, wd, KH * KW * Cin, nullptr, nullptr, dx,
+                         (long long)H * W * Cin, (long long)W * Cin, Cin, Cin, st);
+      if (rc != 0) return rc < 0 ? rc : 0;
+    }
     p.n_tiles = Cin / bn; p.kc_per_tap = Cout / 64;
     p.out = (bf16*)dx; p.alpha = 1.f;
     p.out_sn = (long long)H * W * Cin; p.out_sh = (long long)W * Cin; p.out_sw = Cin;
@@ -184,6 +263,14 @@ int umma_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, in
         continue;
       }
       p.ntaps = nt;
+      {
+        PairTap taps[16];
+        for (int t = 0; t < nt; ++t) taps[t] = PairTap{0, p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
+        rc = try_pair_halo(dy, Cout, Wo, Ho, 1, N, W2, H2, taps, nt, wd, KH * KW * Cin, nullptr, nullptr, outp,
+                           4 * plane_elems, (long long)W2 * Cin, Cin, Cin, st);
+        if (rc < 0) return rc;
+        if (rc == 1) continue;
+      }
       p.n_tiles = Cin / bn; p.kc_per_tap = Cout / 64;
       p.out = outp; p.alpha = 1.f;
       p.out_sn = 4 * plane_elems; p.out_sh = (long long)W2 * Cin; p.out_sw = Cin;
@@ -283,6 +370,7 @@ int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
 int gemm_nt_impl(const void* A, const void* B, const float* bias, const void* residual, void* D, int batch, int M, int Nn,
                  int K, int b_batched, float alpha, cudaStream_t st) {
+  if (pair_enabled() && Nn >= 128) return pair_rows_gemm(A, B, bias, residual, D, batch, M, Nn, K, b_batched, alpha, st);
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.form = 0;
@@ -391,6 +479,13 @@ int narrow_conv(const void* in, const void* pack, const float* bias, void* out, 
       p.tap_dh[t] = sign * (kh - pad_t); p.tap_dw[t] = sign * (kw - pad_l); p.tap_plane[t] = 0;
       p.tap_brow[t] = t * Nout;
     }
+  {
+    PairTap taps[16];
+    for (int t = 0; t < p.ntaps; ++t) taps[t] = PairTap{0, p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
+    int rc = try_pair_halo(in, Kc, W, H, 1, N, W, H, taps, p.ntaps, pack, KH * KW * Nout, bias, nullptr, out,
+                           (long long)H * W * Nout, (long long)W * Nout, Nout, Nout, st);
+    if (rc != 0) return rc < 0 ? rc : 0;
+  }
   p.n_tiles = 1; p.kc_per_tap = Kc / 64;
   p.out = (bf16*)out; p.bias = bias; p.alpha = 1.f;
   p.out_sn = (long long)H * W * Nout; p.out_sh = (long long)W * Nout; p.out_sw = Nout;
@@ -492,6 +587,15 @@ extern "C" int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* 
           p.tap_dh[t] = dh - 1 + a; p.tap_dw[t] = dw - 1 + b; p.tap_plane[t] = 0;
           p.tap_brow[t] = (((a * 2 + b) * 2 + dh) * 2 + dw) * Cout;
         }
+      {
+        PairTap taps[4];
+        for (int t = 0; t < 4; ++t) taps[t] = PairTap{0, p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
+        rc = try_pair_halo(x, Cin, W, H, 1, N, W, H, taps, 4, wf16, 16 * Cout, bias, nullptr,
+                           (bf16*)y + ((long long)a * 2 * W + b) * Cout, 4ll * H * W * Cout, 4ll * W * Cout, 2ll * Cout,
+                           Cout, as_stream(stream));
+        if (rc < 0) return rc;
+        if (rc == 1) continue;
+      }
       p.n_tiles = Cout / bn; p.kc_per_tap = Cin / 64;
       p.out = (bf16*)y + ((long long)a * 2 * W + b) * Cout; p.bias = bias; p.alpha = 1.f;
       p.out_sn = 4ll * H * W * Cout; p.out_sh = 4ll * W * Cout; p.out_sw = 2ll * Cout;
@@ -520,6 +624,13 @@ extern "C" int vcd_upconv2d_dgrad(const void* dy_planes, const void* wd16, void*
     const int dw = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
     p.tap_dh[q] = -(dh - 1 + a); p.tap_dw[q] = -(dw - 1 + b); p.tap_plane[q] = a * 2 + b;
     p.tap_brow[q] = q * Cin;
+  }
+  {
+    PairTap taps[16];
+    for (int t = 0; t < 16; ++t) taps[t] = PairTap{p.tap_plane[t], p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
+    int prc = try_pair_halo(dy_planes, Cout, W, H, 4, N, W, H, taps, 16, wd16, 16 * Cin, nullptr, nullptr, dx,
+                            (long long)H * W * Cin, (long long)W * Cin, Cin, Cin, as_stream(stream));
+    if (prc != 0) return prc < 0 ? prc : 0;
   }
   p.n_tiles = Cin / bn; p.kc_per_tap = Cout / 64;
   p.out = (bf16*)dx; p.alpha = 1.f;

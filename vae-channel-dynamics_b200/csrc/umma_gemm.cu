@@ -11,84 +11,13 @@
 // behind diffusers' Conv2d/Linear/attention, reached from sdxl_vae_wrapper.py:60,71 and
 // train.py:299.
 #include "umma_gemm.cuh"
+#include "umma_ptx.cuh"
 
 namespace {
+using namespace umma;
 
 constexpr int kStageA = 16384;  // 128 rows x 128 B (form 0) or 2 boxes of 64 x 128 B (form 1)
 constexpr int kThreads = 256;
-constexpr long long kSpinLimit = 4000000000LL;  // ~2 s at 2 GHz: turn a deadlock into a trap
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kSpinLimit) {
-      printf("vcd umma_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             bar, parity);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 struct PixTile {
   int w0, h0, n0;
 };
@@ -173,10 +102,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0 && lane == 0) {
-    // ============================== TMA producer ==============================
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  if (warp == 0) {
+    // ============================== TMA producer (warp-uniform loop, one elected lane issues) ==============
+    if (elect_one_sync()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -188,10 +119,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * C::kStageBytes;
-            mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
-            tma_load_5d(sa, &mapA, full_bar(stage), kc * 64, pt.w0 + p.tap_dw[tap], pt.h0 + p.tap_dh[tap],
-                        p.tap_plane[tap], pt.n0);
-            tma_load_5d(sa + kStageA, &mapB, full_bar(stage), kc * 64, brow0 + p.tap_brow[tap], 0, 0, 0);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+              tma_load_5d(sa, &mapA, full_bar(stage), kc * 64, pt.w0 + p.tap_dw[tap], pt.h0 + p.tap_dh[tap],
+                          p.tap_plane[tap], pt.n0);
+              tma_load_5d(sa + kStageA, &mapB, full_bar(stage), kc * 64, brow0 + p.tap_brow[tap], 0, 0, 0);
+            }
+            __syncwarp();
             if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -204,20 +138,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const PixTile pt = decode_pix(p, pix);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::kStageBytes;
-          mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
 #pragma unroll
-          for (int b = 0; b < 2; ++b)
-            tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, pt.w0, pt.h0, p.tap_plane_a[rt.tap], pt.n0);
+            for (int b = 0; b < 2; ++b)
+              tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, pt.w0, pt.h0, p.tap_plane_a[rt.tap],
+                          pt.n0);
 #pragma unroll
-          for (int b = 0; b < BLOCK_N / 64; ++b)
-            tma_load_5d(sa + kStageA + b * 8192, &mapB, full_bar(stage), rt.nt * BLOCK_N + b * 64,
-                        pt.w0 + p.tap_dw[rt.tap], pt.h0 + p.tap_dh[rt.tap], p.tap_plane[rt.tap], pt.n0);
+            for (int b = 0; b < BLOCK_N / 64; ++b)
+              tma_load_5d(sa + kStageA + b * 8192, &mapB, full_bar(stage), rt.nt * BLOCK_N + b * 64,
+                          pt.w0 + p.tap_dw[rt.tap], pt.h0 + p.tap_dh[rt.tap], p.tap_plane[rt.tap], pt.n0);
+          }
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == 1) {
+    // ============================== MMA issuer (warp-uniform loop, one elected lane issues) ==================
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -234,18 +172,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tc_fence_after();
         const uint32_t sa = smem_base + stage * C::kStageBytes;
         const uint32_t sb = sa + kStageA;
-        uint64_t adesc = ((uint64_t)p.a_desc_hi << 32) | (uint64_t)(((sa >> 4) & 0x3FFFu) | (p.a_lbo << 16));
-        uint64_t bdesc = ((uint64_t)p.b_desc_hi << 32) | (uint64_t)(((sb >> 4) & 0x3FFFu) | (p.b_lbo << 16));
+        if (elect_one_sync()) {
+          const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | (p.a_lbo << 16);
+          const uint32_t b_lo = ((sb >> 4) & 0x3FFFu) | (p.b_lbo << 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          umma_bf16(d_tmem, adesc, bdesc, p.idesc, (k | j) != 0 ? 1u : 0u);
-          adesc += p.a_kstep;
-          bdesc += p.b_kstep;
+          for (int j = 0; j < 4; ++j)
+            umma_bf16(d_tmem, ((uint64_t)p.a_desc_hi << 32) | (a_lo + j * p.a_kstep),
+                      ((uint64_t)p.b_desc_hi << 32) | (b_lo + j * p.b_kstep), p.idesc, (k | j) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));  // stage reusable once these MMAs have read it
         }
-        umma_commit(empty_bar(stage));  // stage reusable once these MMAs have read it
+        __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tfull_bar(acc));  // accumulator complete
+      if (elect_one_sync()) umma_commit(tfull_bar(acc));  // accumulator complete
+      __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {

@@ -1,0 +1,424 @@
+// umma_pair.cu — persistent CTA-pair (tcgen05.mma.cta_group::2) implicit-GEMM kernel for sm_100a with
+// shared-memory halo reuse across convolution taps.  See umma_pair.cuh for the operand forms.
+//
+//   warp 0 (1 lane, both CTAs) : TMA producer — A halo box (own 128 pixels) + own half of the B rows, bytes counted
+//                                on the LEADER CTA's mbarrier (cp.async.bulk.tensor...cta_group::2)
+//   warp 1 (1 lane, leader)    : MMA issuer   — tcgen05.mma.cta_group::2.kind::f16, M = 256, N = BLOCK_N;
+//                                tcgen05.commit...multicast::cluster frees stages / publishes accumulators in both CTAs
+//   warp 2 (both CTAs)         : TMEM allocator (tcgen05.alloc.cta_group::2)
+//   warps 4..7 (both CTAs)     : epilogue — tcgen05.ld of the CTA's own 128 TMEM lanes -> alpha/bias/residual ->
+//                                bf16 -> 128-bit global stores; releases the accumulator stage on the leader's barrier
+// Two accumulator stages (2 x BLOCK_N TMEM columns) overlap the epilogue of item i with the main loop of item i+1.
+// Reference arithmetic replaced: the cuDNN/cuBLAS calls behind diffusers' Conv2d / Linear / attention,
+// reached from sdxl_vae_wrapper.py:60,71 and train.py:299.
+#include <stdlib.h>
+#include <string.h>
+
+#include "umma_pair.cuh"
+#include "umma_ptx.cuh"
+
+namespace {
+using namespace umma;
+
+constexpr int kThreads = 384;    // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kABytes = 23552;  // (8+2) x (16+2) rows x 128 B = 23040, rounded up to a multiple of 1024
+constexpr int kBStages = 8;
+
+template <int BLOCK_N>
+struct PCfg {
+  static constexpr int kTapBytes = (BLOCK_N / 2) * 128;  // this CTA's half of one tap's B rows, 64 K-elements each
+  static constexpr int kTapsPerStage = 256 / BLOCK_N;    // a B stage is always 16 KB: 512 MMA cycles per barrier wait
+  static constexpr int kBBytes = kTapBytes * kTapsPerStage;
+  static constexpr int kAStages = (BLOCK_N == 256) ? 3 : 4;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+};
+
+struct TileCoord {
+  int w0, h0, n;  // n = Nimg for a tile past the end (TMA then zero-fills the whole A box)
+  int n_b;        // image whose B rows the pair uses (batched GEMM): never out of range
+  bool valid;
+};
+__device__ __forceinline__ TileCoord decode_tile(const PairParams& p, int pair, int rank) {
+  const int per_n = p.tiles_w * p.tiles_h;
+  int n, lt;
+  bool valid;
+  if (p.pair_in_image) {
+    const int ppn = (per_n + 1) >> 1;
+    n = pair / ppn;
+    lt = (pair - n * ppn) * 2 + rank;
+    valid = lt < per_n;
+  } else {
+    const int t = pair * 2 + rank;
+    valid = t < p.pix_tiles;
+    n = t / per_n;
+    lt = t - n * per_n;
+  }
+  TileCoord c;
+  const int tw = lt % p.tiles_w, th = lt / p.tiles_w;
+  c.w0 = tw * (p.mode ? 128 : 8);
+  c.h0 = th * (p.mode ? 1 : 16);
+  c.n = valid ? n : p.Nimg;  // an out-of-range image index makes TMA zero-fill the whole box
+  c.n_b = n < p.Nimg ? n : p.Nimg - 1;
+  c.valid = valid;
+  return c;
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ PairParams p) {
+  using C = PCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + C::kAStages * kABytes;
+  const uint32_t bar_base = b_base + kBStages * C::kBBytes;
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (C::kAStages + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * C::kAStages + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * C::kAStages + kBStages + s); };
+  auto tfull = [&](int s) { return bar_base + 8u * (2 * C::kAStages + 2 * kBStages + s); };
+  auto tempty = [&](int s) { return bar_base + 8u * (2 * C::kAStages + 2 * kBStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kAStages + 2 * kBStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kAStages; ++s) {
+      mbar_init(afull(s), 1);
+      mbar_init(aempty(s), 1);
+    }
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull(s), 1);
+      mbar_init(tempty(s), 2 * kEpiWarps);  // epilogue warps of both CTAs (only the leader's copy is waited on)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs; warp-uniform, one elected lane issues) ==========
+    if (elect_one_sync()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      const int nt = item % p.n_tiles;
+      const TileCoord tc = decode_tile(p, item / p.n_tiles, rank);
+      const int brow0 = nt * BLOCK_N + rank * (BLOCK_N / 2) + tc.n_b * p.b_batch_rows;
+      for (int kc = 0; kc < p.kc; ++kc) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          mbar_wait(aempty(sa), pa ^ 1u);
+          if (elect_one_sync()) {
+            if (rank == 0) mbar_arrive_expect_tx(afull(sa), 2u * p.a_box_bytes);
+            tma_load_5d_pair(a_base + sa * kABytes, &mapA, afull(sa) & kPeerBitMask, kc * 64, tc.w0 + p.g_dw[g],
+                             tc.h0 + p.g_dh[g], p.g_plane[g], tc.n);
+          }
+          __syncwarp();
+          if (++sa == C::kAStages) { sa = 0; pa ^= 1u; }
+          for (int tap = p.g_tap0[g]; tap < p.g_tap0[g + 1]; tap += C::kTapsPerStage) {
+            const int nt_here = min(C::kTapsPerStage, p.g_tap0[g + 1] - tap);
+            mbar_wait(bempty(sb), pb ^ 1u);
+            if (elect_one_sync()) {
+              if (p.dbg & 8) {  // profiling aid: no B traffic (stale shared memory is multiplied)
+                if (rank == 0) mbar_arrive(bfull(sb));
+              } else {
+                if (rank == 0) mbar_arrive_expect_tx(bfull(sb), 2u * (uint32_t)(nt_here * C::kTapBytes));
+                for (int u = 0; u < nt_here; ++u)
+                  tma_load_5d_pair(b_base + sb * C::kBBytes + u * C::kTapBytes, &mapB, bfull(sb) & kPeerBitMask,
+                                   kc * 64, brow0 + p.tap_brow[tap + u], 0, 0, 0);
+              }
+            }
+            __syncwarp();
+            if (++sb == kBStages) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ============================== MMA issuer (leader CTA; warp-uniform, one elected lane issues) ===========
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pa = 0, pb = 0, acc_phase = 0;
+    const uint32_t a_hi = (uint32_t)((p.mode ? 1024 : p.box_w * 128) >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      mbar_wait(tempty(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+      uint32_t accum = 0;
+      for (int kc = 0; kc < p.kc; ++kc) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          mbar_wait(afull(sa), pa);
+          tc_fence_after();
+          const uint32_t sa_addr = a_base + sa * kABytes;
+          for (int tap = p.g_tap0[g]; tap < p.g_tap0[g + 1]; tap += C::kTapsPerStage) {
+            const int nt_here = min(C::kTapsPerStage, p.g_tap0[g + 1] - tap);
+            mbar_wait(bfull(sb), pb);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              for (int u = 0; u < nt_here; ++u) {
+                const uint32_t a0 = sa_addr + (uint32_t)p.tap_aoff[tap + u];
+                const uint32_t b0 = b_base + sb * C::kBBytes + u * C::kTapBytes;
+                const uint32_t a_lo = ((a0 >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t b_lo = ((b0 >> 4) & 0x3FFFu) | (1u << 16);
+                if (!(p.dbg & 2)) {
+                  // K advances 16 bf16 = 32 B (descriptor units of 16 B: +2) inside the 128-byte swizzle row
+                  umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
+                  umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), p.idesc, 1u);
+                  umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 4), ((uint64_t)b_hi << 32) | (b_lo + 4), p.idesc, 1u);
+                  umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 6), ((uint64_t)b_hi << 32) | (b_lo + 6), p.idesc, 1u);
+                }
+                accum = 1u;
+              }
+              umma_commit_pair(bempty(sb));
+            }
+            __syncwarp();
+            accum = 1u;
+            if (++sb == kBStages) { sb = 0; pb ^= 1u; }
+          }
+          if (elect_one_sync()) umma_commit_pair(aempty(sa));
+          __syncwarp();
+          if (++sa == C::kAStages) { sa = 0; pa ^= 1u; }
+        }
+      }
+      if (elect_one_sync()) umma_commit_pair(tfull(acc));
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue (both CTAs) ==============================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int chalf = (warp - 4) >> 2;      // which half of the BLOCK_N columns
+    const int row = q * 32 + lane;
+    const int tile_w = p.mode ? 128 : 8;
+    const int wi = row % tile_w, hi = row / tile_w;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      const int nt = item % p.n_tiles;
+      const TileCoord tc = decode_tile(p, item / p.n_tiles, rank);
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const int w = tc.w0 + wi, h = tc.h0 + hi;
+      const bool valid = tc.valid && (w < p.W) && (h < p.H);
+      const long long off =
+          (long long)tc.n * p.out_sn + (long long)h * p.out_sh + (long long)w * p.out_sw + nt * BLOCK_N;
+#pragma unroll 1
+      for (int ch = chalf * (BLOCK_N / 64); ch < (chalf + 1) * (BLOCK_N / 64); ++ch) {
+        if (p.dbg & 1) break;
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        tmem_wait_ld();
+        const int col0 = nt * BLOCK_N + ch * 32;
+        if (valid && col0 < p.Nout && !(p.dbg & 4)) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (p.bias) {
+            const float* bp = p.bias + col0;
+            if (col0 + 32 <= p.Nout) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.Nout) v[j] += __ldg(bp + j);
+            }
+          }
+          if (p.residual) {
+            const bf16* rp = p.residual + off + ch * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+              if (col0 + g * 8 + 8 > p.Nout) continue;
+              unpack8(ld8(rp + g * 8), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+            }
+          }
+          bf16* op = p.out + off + ch * 32;
+          if ((p.Nout & 7) == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (col0 + g * 8 < p.Nout) st8(op + g * 8, pack8(v + g * 8));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Nout) op[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty(acc) & kPeerBitMask);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the leader's MMAs read the peer's shared memory; nobody leaves before both are done
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+  }
+}
+
+uint32_t pair_idesc(int n) {
+  // kind::f16: D = f32, A = B = bf16, both K-major, N >> 3, M = 256 >> 4
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
+}  // namespace
+
+bool pair_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VCD_PAIR");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+bool pair_setup_halo(PairParams& p, int W, int H, int N, const PairTap* taps, int ntaps, int block_n, int* box_h_out) {
+  if (W < 8 || H < 16 || ntaps < 1 || ntaps > 16) return false;
+  p.mode = 0;
+  p.W = W; p.H = H; p.Nimg = N;
+  p.tiles_w = (W + 7) / 8;
+  p.tiles_h = (H + 15) / 16;
+  p.pix_tiles = p.tiles_w * p.tiles_h * N;
+  p.pair_in_image = 0;
+  p.pairs = (p.pix_tiles + 1) / 2;
+  // groups = distinct planes, in order of first appearance
+  int ng = 0, gmin_h[4], gmin_w[4], gmax_h[4], gmax_w[4], tap_group[16];
+  for (int t = 0; t < ntaps; ++t) {
+    int g = -1;
+    for (int k = 0; k < ng; ++k)
+      if (p.g_plane[k] == taps[t].plane) g = k;
+    if (g < 0) {
+      if (ng == 4) return false;
+      g = ng++;
+      p.g_plane[g] = taps[t].plane;
+      gmin_h[g] = gmax_h[g] = taps[t].dh;
+      gmin_w[g] = gmax_w[g] = taps[t].dw;
+    }
+    tap_group[t] = g;
+    if (taps[t].dh < gmin_h[g]) gmin_h[g] = taps[t].dh;
+    if (taps[t].dh > gmax_h[g]) gmax_h[g] = taps[t].dh;
+    if (taps[t].dw < gmin_w[g]) gmin_w[g] = taps[t].dw;
+    if (taps[t].dw > gmax_w[g]) gmax_w[g] = taps[t].dw;
+  }
+  int halo_h = 0, halo_w = 0;
+  for (int g = 0; g < ng; ++g) {
+    if (gmax_h[g] - gmin_h[g] > halo_h) halo_h = gmax_h[g] - gmin_h[g];
+    if (gmax_w[g] - gmin_w[g] > halo_w) halo_w = gmax_w[g] - gmin_w[g];
+  }
+  if (halo_h > 2 || halo_w > 2) return false;
+  p.ngroups = ng;
+  p.box_w = 8 + halo_w;
+  *box_h_out = 16 + halo_h;
+  p.a_box_bytes = (uint32_t)(p.box_w * (16 + halo_h) * 128);
+  int k = 0;
+  for (int g = 0; g < ng; ++g) {
+    p.g_dh[g] = gmin_h[g];
+    p.g_dw[g] = gmin_w[g];
+    p.g_tap0[g] = k;
+    for (int t = 0; t < ntaps; ++t)
+      if (tap_group[t] == g) {
+        p.tap_aoff[k] = ((taps[t].dh - gmin_h[g]) * p.box_w + (taps[t].dw - gmin_w[g])) * 128;
+        p.tap_brow[k] = taps[t].brow;
+        ++k;
+      }
+  }
+  p.g_tap0[ng] = k;
+  p.ntaps = ntaps;
+  p.idesc = pair_idesc(block_n);
+  return true;
+}
+
+void pair_setup_rows(PairParams& p, int rows, int batch, int pair_in_image, int brow, int block_n) {
+  p.mode = 1;
+  p.W = rows; p.H = 1; p.Nimg = batch;
+  p.tiles_w = (rows + 127) / 128;
+  p.tiles_h = 1;
+  p.pix_tiles = p.tiles_w * batch;
+  p.pair_in_image = pair_in_image;
+  p.pairs = pair_in_image ? ((p.tiles_w + 1) / 2) * batch : (p.pix_tiles + 1) / 2;
+  p.box_w = 128;
+  p.a_box_bytes = 128 * 128;
+  p.ngroups = 1;
+  p.g_plane[0] = 0; p.g_dh[0] = 0; p.g_dw[0] = 0;
+  p.g_tap0[0] = 0; p.g_tap0[1] = 1;
+  p.ntaps = 1;
+  p.tap_aoff[0] = 0;
+  p.tap_brow[0] = brow;
+  p.idesc = pair_idesc(block_n);
+}
+
+static long long g_pair_launches = 0;
+extern "C" int64_t vcd_pair_kernel_launches(void) { return g_pair_launches; }
+
+int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p, int block_n, cudaStream_t st) {
+  p.total_items = p.pairs * p.n_tiles;
+  if (p.total_items <= 0) return 0;
+  ++g_pair_launches;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VCD_PAIR_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
+  const int max_clusters = vcd_num_sms() / 2;
+  const int clusters = p.total_items < max_clusters ? p.total_items : max_clusters;
+  const int grid = clusters * 2;
+  if (block_n == 256) {
+    static bool attr = false;
+    if (!attr) {
+      VCD_CUDA(cudaFuncSetAttribute(umma_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    PCfg<256>::kSmemBytes));
+      attr = true;
+    }
+    umma_pair_kernel<256><<<grid, kThreads, PCfg<256>::kSmemBytes, st>>>(mapA, mapB, p);
+  } else if (block_n == 128) {
+    static bool attr = false;
+    if (!attr) {
+      VCD_CUDA(cudaFuncSetAttribute(umma_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    PCfg<128>::kSmemBytes));
+      attr = true;
+    }
+    umma_pair_kernel<128><<<grid, kThreads, PCfg<128>::kSmemBytes, st>>>(mapA, mapB, p);
+  } else {
+    vcd_set_error("pair_launch: BLOCK_N %d unsupported", block_n);
+    return -1;
+  }
+  VCD_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,59 @@
+// umma_pair.cuh — host-visible description of the CTA-pair (cta_group::2) implicit-GEMM kernel (umma_pair.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+// D[pixel][n] = alpha * sum_{tap} sum_{c} A[pixel + shift(tap)][c] * B[tap_brow + n][c]  (+bias, +residual)
+//
+// Two CTAs of a cluster (an SM pair) execute ONE tcgen05.mma.cta_group::2 stream: M = 256 (128 pixels per CTA),
+// N = BLOCK_N; each CTA stages its own 128-pixel A operand and HALF of the B operand (BLOCK_N/2 weight rows), so
+// the weight traffic from L2 and the shared-memory reads per FLOP are half those of a single-CTA tile.
+//
+// HALO mode (3x3 / 2x2-phase / stride-2 convolutions): a CTA's pixel tile is 8 (w) x 16 (h) pixels of one image.
+// For every 64-channel K chunk ONE TMA box of (8+halo_w) x (16+halo_h) pixels is loaded and ALL taps that read the
+// same tensor plane are served from it: the A descriptor of a tap starts (dh*box_w + dw) 128-byte rows into the
+// box and strides box_w*128 bytes between its 8-row groups (the 128B swizzle is a function of the absolute
+// shared-memory address, so a row-shifted start is legal — tools/probe_umma.py).  The activation is read from L2
+// ~1.4x instead of 9x per 3x3 convolution.
+// ROWS mode (1x1 convolutions, Linear, Q.K^T, P.V): the pixel space is a flat list of rows, tile = 128 rows, one tap.
+struct PairParams {
+  int mode;              // 0 = HALO, 1 = ROWS
+  int W, H, Nimg;        // pixel space; ROWS: W = rows per batch entry, H = 1, Nimg = batch entries
+  int tiles_w, tiles_h;  // tiles per image
+  int pix_tiles;         // tiles_w * tiles_h * Nimg
+  int pair_in_image;     // 1: both tiles of a pair lie in the same image (per-image B operand)
+  int pairs;             // pair-tiles
+  int n_tiles;           // ceil(Nout / BLOCK_N)
+  int total_items;       // pairs * n_tiles
+  int box_w;             // A box width in pixels (HALO: 8 + halo_w, ROWS: 128)
+  uint32_t a_box_bytes;  // bytes of one A box
+  int ngroups;           // A boxes per K chunk (one per tensor plane the taps touch)
+  int g_plane[4], g_dh[4], g_dw[4];  // plane and origin offset of each group's box relative to the tile origin
+  int g_tap0[5];         // taps [g_tap0[g], g_tap0[g+1]) belong to group g
+  int ntaps;
+  int tap_aoff[16];      // byte offset of the tap's first row inside its group's box
+  int tap_brow[16];      // B row offset of the tap
+  int kc;                // 64-channel K chunks per tap
+  int b_batch_rows;      // B row offset per image (batched GEMM); 0 = shared weights
+  bf16* out;
+  const bf16* residual;
+  const float* bias;
+  float alpha;
+  long long out_sn, out_sh, out_sw;  // element strides of (n, h, w) in out / residual
+  int Nout;
+  uint32_t idesc;
+  int dbg;  // profiling aid (VCD_PAIR_DBG): 1 = epilogue only hand-shakes, 2 = MMA warp issues no MMAs, 4 = no stores
+};
+
+struct PairTap {
+  int plane, dh, dw, brow;
+};
+
+// fills mode / tiling / groups / taps / descriptors of a HALO launch; returns false when the shape is not eligible
+bool pair_setup_halo(PairParams& p, int W, int H, int N, const PairTap* taps, int ntaps, int block_n, int* box_h_out);
+void pair_setup_rows(PairParams& p, int rows, int batch, int pair_in_image, int brow, int block_n);
+int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p, int block_n, cudaStream_t st);
+bool pair_enabled();
