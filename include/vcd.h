@@ -60,9 +60,12 @@ int vcd_pack_conv_weight(const void* w, const void* bias, int dtype, int Cout, i
  * past the bottom/right edge).  x_planes != 0 (stride 2 only) means x is the parity-plane
  * layout [N][2][2][H/2][W/2][C] written by vcd_space_to_planes. */
 int64_t vcd_conv2d_fprop_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
+/* gn_sums (fp64 [N][gn_groups][2], may be NULL): on return holds sum and sum of squares of y per (image, group) —
+ * the statistics the GroupNorm that consumes y needs (vcd_gn_apply_fwd), produced by the GEMM epilogue when the
+ * tcgen05 pair kernel serves the layer (no extra pass over y), otherwise by vcd_gn_stats inside the call. */
 int vcd_conv2d_fprop(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y, void* ws,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
-                     int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream);
+                     int Ho, int Wo, int x_planes, int impl, double* gn_sums, int gn_groups, vcd_stream_t stream);
 /* dx = conv_transpose(dy).  dx_planes != 0 (stride 2 only): dx is written in parity-plane layout. */
 int64_t vcd_conv2d_dgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
 int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void* w_dgrad, void* dx, void* ws,
@@ -84,7 +87,7 @@ int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, const fl
 int vcd_pack_upconv_weight(const void* w, const void* bias, int dtype, int Cout, int Cin, void* wf16, void* wd16,
                            float* bias_f32, vcd_stream_t stream);
 int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* bias, void* y, int N, int H, int W, int Cin,
-                       int Cout, vcd_stream_t stream);
+                       int Cout, double* gn_sums, int gn_groups, vcd_stream_t stream);
 int vcd_upconv2d_dgrad(const void* dy_planes, const void* wd16, void* dx, int N, int H, int W, int Cin, int Cout,
                        vcd_stream_t stream);
 int64_t vcd_upconv2d_wgrad_ws_bytes(int Cin, int Cout);

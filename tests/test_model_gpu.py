@@ -249,14 +249,24 @@ def test_graphed_step_matches_eager_step(vcd, pair, monkeypatch):
     t2, r2, k2 = g.step(x)
     assert g.launches_per_replay > 300
     assert abs(float(r2) - float(rec)) < 2e-2 * float(rec) and abs(float(k2) - float(kl)) < 2e-2 * float(kl)
-    cos = []
+    # per-parameter direction agreement (bf16 kernels with fp32 atomics are not bit-reproducible run to run, so
+    # parameters whose gradient is numerically negligible are excluded), and agreement of the whole gradient vector
+    norms = {n: float(eager[n].norm()) for n in eager}
+    big = max(norms.values())
+    low = []
     for n, p in w.named_parameters():
         a, b = p.grad.detach().float().flatten(), eager[n].flatten()
-        if a.numel() >= 512:
-            cos.append(float(torch.nn.functional.cosine_similarity(a, b, dim=0)))
-    assert min(cos) > 0.9 and sum(cos) / len(cos) > 0.98, (min(cos), sum(cos) / len(cos))
+        if a.numel() >= 512 and norms[n] > 1e-3 * big:
+            c = float(torch.nn.functional.cosine_similarity(a, b, dim=0))
+            if c < 0.9:
+                low.append((n, c, norms[n]))
+    assert not low, low
+    ga = torch.cat([p.grad.detach().float().flatten() for _, p in w.named_parameters()])
+    gb = torch.cat([eager[n].flatten() for n, _ in w.named_parameters()])
+    assert float(torch.nn.functional.cosine_similarity(ga, gb, dim=0)) > 0.99
     # the graph repacks weights on every replay: change a weight, replay, the loss must move
+    r2_value = float(r2)          # step() returns the graph's static output tensors: read before the next replay
     with torch.no_grad():
         w.vae.decoder.conv_out.weight.mul_(3.0)
     _, r3, _ = g.step(x)
-    assert abs(float(r3) - float(r2)) > 1e-3 * float(r2)
+    assert abs(float(r3) - r2_value) > 1e-3 * r2_value

@@ -171,3 +171,40 @@ def test_upconv_pair_kernel(vcd):
     test_upconv_fused_matches_torch(vcd, 2, 32, 16, 256, 256)
     test_upconv_fused_matches_torch(vcd, 1, 16, 24, 512, 512)
     assert lib.vcd_pair_kernel_launches() >= n0 + 10   # 4 phase fprops + 1 dgrad per call
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,fused", [
+    (2, 32, 16, 128, 128, 3, True),     # D = 4 channels per group
+    (3, 16, 8, 256, 256, 3, True),      # D = 8, odd tile count
+    (1, 40, 24, 128, 512, 3, True),     # D = 16, ragged tiles, two n-tiles
+    (2, 16, 16, 256, 128, 1, True),     # 1x1 shortcut (ROWS mode, 256 rows per image)
+    (2, 12, 10, 128, 128, 3, False),    # not eligible for the pair kernel: sums from vcd_gn_stats inside the call
+])
+def test_conv_epilogue_groupnorm_sums(vcd, N, H, W, cin, cout, k, fused):
+    """gn_sums of vcd_conv2d_fprop: sum / sum of squares of the bf16 output per (image, group), whichever path
+    serves the layer, equal the sums of the stored tensor (the GroupNorm that follows never re-reads it)."""
+    ops, lib = vcd.ops, vcd._lib.lib()
+    x = torch.randn(N, H, W, cin, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(cout, cin, k, k, device="cuda") / math.sqrt(cin * k * k)).to(torch.bfloat16)
+    b = torch.randn(cout, device="cuda").to(torch.bfloat16)
+    res = torch.randn(N, H, W, cout, device="cuda").to(torch.bfloat16)
+    n0 = lib.vcd_pair_kernel_launches()
+    y = ops.conv2d(x, w, b, ops.PackedWeights(), pad_t=k // 2, pad_l=k // 2, residual=res, gn_groups=32)
+    assert (lib.vcd_pair_kernel_launches() > n0) == fused
+    sums = ops.pop_gn_sums(y, 32)
+    assert sums is not None
+    yf = y.double().reshape(N, H * W, 32, cout // 32)
+    ref = torch.stack([yf.sum(dim=(1, 3)), (yf * yf).sum(dim=(1, 3))], dim=-1).reshape(-1)
+    assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-3), float((sums - ref).abs().max())
+
+
+def test_upconv_epilogue_groupnorm_sums(vcd):
+    ops = vcd.ops
+    x = torch.randn(2, 16, 16, 256, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(256, 256, 3, 3, device="cuda") / 48.0).to(torch.bfloat16)
+    b = torch.randn(256, device="cuda").to(torch.bfloat16)
+    y = ops.upconv2d(x, w, b, ops.UpconvPackedWeights(), 32)
+    sums = ops.pop_gn_sums(y, 32)
+    yf = y.double().reshape(2, 32 * 32, 32, 8)
+    ref = torch.stack([yf.sum(dim=(1, 3)), (yf * yf).sum(dim=(1, 3))], dim=-1).reshape(-1)
+    assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-3), float((sums - ref).abs().max())

@@ -38,7 +38,7 @@ for sh in a.shapes:
 
     def fprop(i):
         call("vcd_conv2d_fprop", _p(xs[i % nbuf]), _p(wf), _p(b32), None, _p(y), None, B, h, h, ci, co, k, k, 1, pad, pad, h, h,
-             0, 0, _st())
+             0, 0, None, 0, _st())
 
     def dgrad(i):
         call("vcd_conv2d_dgrad", _p(gs[i % nbuf]), _p(wf), _p(wd), _p(dx), None, B, h, h, ci, co, k, k, 1, pad, pad, h, h, 0, 0,

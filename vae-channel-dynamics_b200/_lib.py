@@ -20,13 +20,13 @@ SIGNATURES = {
     "vcd_conv_umma_supported": (_i, [_i] * 5),
     "vcd_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "vcd_conv2d_fprop_ws_bytes": (_i64, [_i] * 8),
-    "vcd_conv2d_fprop": (_i, [_p] * 6 + [_i] * 14 + [_p]),
+    "vcd_conv2d_fprop": (_i, [_p] * 6 + [_i] * 14 + [_p, _i, _p]),
     "vcd_conv2d_dgrad_ws_bytes": (_i64, [_i] * 8),
     "vcd_conv2d_dgrad": (_i, [_p] * 5 + [_i] * 14 + [_p]),
     "vcd_conv2d_wgrad_ws_bytes": (_i64, [_i] * 8),
     "vcd_conv2d_wgrad": (_i, [_p] * 5 + [_i] + [_p] + [_i] * 14 + [_p]),
     "vcd_pack_upconv_weight": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
-    "vcd_upconv2d_fprop": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "vcd_upconv2d_fprop": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "vcd_upconv2d_dgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vcd_upconv2d_wgrad_ws_bytes": (_i64, [_i, _i]),
     "vcd_upconv2d_wgrad": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p]),

@@ -86,10 +86,22 @@ int pair_block_n(int pairs, int Nout) {
   (void)pairs;
   return (Nout % 256 != 0) ? 128 : 256;
 }
+// attach the fused GroupNorm-sum epilogue when the output shape allows it (zeroes the sums buffer)
+int attach_gn(PairParams& p, GnEpilogue* gn, int n_images, int Nout, int rows_per_img, cudaStream_t st) {
+  if (!gn || !gn->sums || gn->groups <= 0 || Nout % gn->groups != 0) return 0;
+  const int D = Nout / gn->groups;
+  const int logD = D == 4 ? 2 : D == 8 ? 3 : D == 16 ? 4 : -1;
+  if (logD < 0 || Nout % 32 != 0) return 0;
+  if (p.mode == 1 && (rows_per_img <= 0 || rows_per_img % 128 != 0)) return 0;
+  p.gn_sums = gn->sums; p.gn_G = gn->groups; p.gn_logD = logD; p.gn_rows_per_img = rows_per_img;
+  if (!gn->accumulate) VCD_CUDA(cudaMemsetAsync(gn->sums, 0, sizeof(double) * 2 * n_images * gn->groups, st));
+  gn->fused = true;
+  return 0;
+}
 // implicit-GEMM convolution with halo reuse: returns 1 when launched, 0 when the shape is not eligible, < 0 on error
 int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, int Ht, const PairTap* taps, int ntaps,
                   const void* wpack, int wrows, const float* bias, const void* residual, void* out, long long sn,
-                  long long sh, long long sw, int Nout, cudaStream_t st) {
+                  long long sh, long long sw, int Nout, cudaStream_t st, GnEpilogue* gn = nullptr) {
   if (!pair_enabled() || C % 64 != 0) return 0;
   PairParams p;
   memset(&p, 0, sizeof(p));
@@ -104,6 +116,7 @@ int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, 
   p.Nout = Nout;
   CUtensorMap mA, mB;
   int rc;
+  if ((rc = attach_gn(p, gn, N, Nout, 0, st))) return rc;
   if ((rc = make_act_map(&mA, act, C, Wa, Ha, P, N, 64, p.box_w, box_h, 1))) return rc;
   if ((rc = make_act_map(&mB, wpack, C, wrows, 1, 1, 1, 64, bn / 2, 1, 1))) return rc;
   if ((rc = pair_launch(mA, mB, p, bn, st))) return rc;
@@ -111,7 +124,8 @@ int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, 
 }
 // plain GEMM rows x Nout (1x1 convolutions, Linear, attention products): D[b][m][n] = alpha * A[b][m][:] . B[(b)][n][:]
 int pair_rows_gemm(const void* A, const void* B, const float* bias, const void* residual, void* D, int batch, int M, int Nn,
-                   int K, int b_batched, float alpha, cudaStream_t st) {
+                   int K, int b_batched, float alpha, cudaStream_t st, GnEpilogue* gn = nullptr, int gn_images = 0,
+                   int gn_rows_per_img = 0) {
   PairParams p;
   memset(&p, 0, sizeof(p));
   const int tiles = (M + 127) / 128;
@@ -126,6 +140,7 @@ int pair_rows_gemm(const void* A, const void* B, const float* bias, const void* 
   p.Nout = Nn;
   CUtensorMap mA, mB;
   int rc;
+  if ((rc = attach_gn(p, gn, gn_images, Nn, gn_rows_per_img, st))) return rc;
   if ((rc = make_act_map(&mA, A, K, M, 1, 1, batch, 64, 128, 1, 1))) return rc;
   if ((rc = make_act_map(&mB, B, K, b_batched ? batch * Nn : Nn, 1, 1, 1, 64, bn / 2, 1, 1))) return rc;
   return pair_launch(mA, mB, p, bn, st);
@@ -157,7 +172,7 @@ bool umma_shape_ok(int Cin, int Cout, int KH, int KW, int stride) {
 
 int umma_fprop(const void* x, const void* wf, const float* bias, const void* residual, void* y, int N, int H, int W,
                int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, int x_planes,
-               cudaStream_t st) {
+               cudaStream_t st, GnEpilogue* gn = nullptr) {
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.form = 0;
@@ -170,14 +185,14 @@ int umma_fprop(const void* x, const void* wf, const float* bias, const void* res
     int rc;
     if (KH * KW == 1 && stride == 1) {  // 1x1 shortcut: a plain GEMM over all pixels
       VCD_CHECK_ARG((long long)N * H * W < (1ll << 31), "1x1 conv: too many pixels");
-      return pair_rows_gemm(x, wf, bias, residual, y, 1, N * H * W, Cout, Cin, 0, 1.f, st);
+      return pair_rows_gemm(x, wf, bias, residual, y, 1, N * H * W, Cout, Cin, 0, 1.f, st, gn, N, H * W);
     }
     PairTap taps[16];
     for (int t = 0; t < p.ntaps; ++t) taps[t] = PairTap{p.tap_plane[t], p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
     rc = stride == 1 ? try_pair_halo(x, Cin, W, H, 1, N, Wo, Ho, taps, p.ntaps, wf, KH * KW * Cout, bias, residual, y,
-                                     (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st)
+                                     (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st, gn)
                      : try_pair_halo(x, Cin, W / 2, H / 2, 4, N, Wo, Ho, taps, p.ntaps, wf, KH * KW * Cout, bias, residual,
-                                     y, (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st);
+                                     y, (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st, gn);
     if (rc != 0) return rc < 0 ? rc : 0;
   }
   p.n_tiles = Cout / bn;
@@ -568,12 +583,14 @@ extern "C" int vcd_pack_upconv_weight(const void* w, const void* bias, int dtype
 
 // x [N][H][W][Cin] -> y [N][2H][2W][Cout]
 extern "C" int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* bias, void* y, int N, int H, int W,
-                                  int Cin, int Cout, vcd_stream_t stream) {
+                                  int Cin, int Cout, double* gn_sums, int gn_groups, vcd_stream_t stream) {
   VCD_CHECK_ARG(x && wf16 && y, "upconv fprop: null pointer");
   VCD_CHECK_ARG(Cin % 128 == 0 && Cout % 128 == 0, "upconv: channels must be multiples of 128 (Cin=%d Cout=%d)", Cin, Cout);
   const int bn = pick_block_n(Cout);
   CUtensorMap mA, mB;
   int rc;
+  // GroupNorm sums of y accumulate over the four phase launches (the first one zeroes the buffer)
+  bool all_fused = gn_sums != nullptr;
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
       UmmaParams p;
@@ -590,11 +607,13 @@ extern "C" int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* 
       {
         PairTap taps[4];
         for (int t = 0; t < 4; ++t) taps[t] = PairTap{0, p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
+        GnEpilogue gph{gn_sums, gn_groups, false, (a | b) != 0};
         rc = try_pair_halo(x, Cin, W, H, 1, N, W, H, taps, 4, wf16, 16 * Cout, bias, nullptr,
                            (bf16*)y + ((long long)a * 2 * W + b) * Cout, 4ll * H * W * Cout, 4ll * W * Cout, 2ll * Cout,
-                           Cout, as_stream(stream));
+                           Cout, as_stream(stream), (gn_sums && all_fused) ? &gph : nullptr);
         if (rc < 0) return rc;
-        if (rc == 1) continue;
+        if (rc == 1) { all_fused = all_fused && gph.fused; continue; }
+        all_fused = false;
       }
       p.n_tiles = Cout / bn; p.kc_per_tap = Cin / 64;
       p.out = (bf16*)y + ((long long)a * 2 * W + b) * Cout; p.bias = bias; p.alpha = 1.f;
@@ -606,6 +625,7 @@ extern "C" int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* 
       if ((rc = make_act_map(&mB, wf16, Cin, 16 * Cout, 1, 1, 1, 64, bn, 1, 1))) return rc;
       if ((rc = umma_launch(mA, mB, p, bn, as_stream(stream)))) return rc;
     }
+  if (gn_sums && !all_fused) return vcd_gn_stats(y, gn_sums, nullptr, 0.f, N, 4 * H * W, Cout, gn_groups, stream);
   return 0;
 }
 
@@ -729,16 +749,36 @@ extern "C" int64_t vcd_conv2d_dgrad_ws_bytes(int N, int H, int W, int Cin, int C
   return dgrad_path(Cin, Cout, KH, KW, stride) == 4 ? patch_gemm_ws((int64_t)N * H * W, Cout, Cin, KH * KW) : 0;
 }
 
+static int conv_fprop_impl(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y, void* ws,
+                           int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int Ho,
+                           int Wo, int x_planes, int impl, GnEpilogue* gn, cudaStream_t st);
+
 extern "C" int vcd_conv2d_fprop(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y,
                                 void* ws, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t,
-                                int pad_l, int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream) {
+                                int pad_l, int Ho, int Wo, int x_planes, int impl, double* gn_sums, int gn_groups,
+                                vcd_stream_t stream) {
   VCD_CHECK_ARG(x && w_fprop && y, "conv fprop: null pointer");
   cudaStream_t st = as_stream(stream);
+  if (gn_sums) {  // GroupNorm sums of y: fused into the GEMM epilogue when the pair kernel serves the layer
+    GnEpilogue gn{gn_sums, gn_groups, false};
+    const int rc = conv_fprop_impl(x, w_fprop, bias, residual, y, ws, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho,
+                                   Wo, x_planes, impl, &gn, st);
+    if (rc || gn.fused) return rc;
+    return vcd_gn_stats(y, gn_sums, nullptr, 0.f, N, Ho * Wo, Cout, gn_groups, stream);
+  }
+  return conv_fprop_impl(x, w_fprop, bias, residual, y, ws, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo,
+                         x_planes, impl, nullptr, st);
+}
+
+static int conv_fprop_impl(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y, void* ws,
+                           int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l, int Ho,
+                           int Wo, int x_planes, int impl, GnEpilogue* gn, cudaStream_t st) {
   const int path = impl == VCD_IMPL_SIMT ? 1 : fprop_path(Cin, Cout, KH, KW, stride);
   if (impl == VCD_IMPL_UMMA)
     VCD_CHECK_ARG(path != 1, "conv fprop: shape (Cin=%d,Cout=%d,k=%d,s=%d) has no tcgen05 path", Cin, Cout, KH, stride);
   if (path == 2)
-    return umma_fprop(x, w_fprop, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, x_planes, st);
+    return umma_fprop(x, w_fprop, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, x_planes, st,
+                      gn);
   VCD_CHECK_ARG(!x_planes, "conv fprop: parity-plane input only on the tcgen05 stride-2 path");
   if (path == 3 && !residual)
     return narrow_conv(x, w_fprop, bias, y, N, H, W, Cin, Cout, KH, KW, pad_t, pad_l, +1, st);

@@ -36,15 +36,17 @@ struct RedTile {
   int batch, tap, mt, nt, k0, nk;
 };
 __device__ __forceinline__ RedTile decode_red(const UmmaParams& p, int t) {
+  // taps fastest: the CTAs running at the same time work on the SAME pixel range for all taps / channel tiles, so
+  // the activation and gradient tiles are read from DRAM once and served from L2 to the other taps
   RedTile r;
-  int split = t % p.splits;
-  int q = t / p.splits;
+  r.tap = t % p.ntaps;
+  int q = t / p.ntaps;
   r.nt = q % p.n_tiles;
   q /= p.n_tiles;
   r.mt = q % p.m_tiles;
   q /= p.m_tiles;
-  r.tap = q % p.ntaps;
-  r.batch = q / p.ntaps;
+  int split = q % p.splits;
+  r.batch = q / p.splits;
   r.k0 = split * p.k_per_split;
   int k1 = min(r.k0 + p.k_per_split, p.k_tiles);
   r.nk = k1 - r.k0;

@@ -65,6 +65,41 @@ __device__ __forceinline__ TileCoord decode_tile(const PairParams& p, int pair, 
   return c;
 }
 
+// per-thread partial GroupNorm sums of one 32-column chunk: vals[2g] = sum, vals[2g+1] = sum of squares of the
+// bf16-rounded outputs of group g (D = 1 << LOGD channels per group, 32 / D groups per chunk)
+template <int LOGD>
+__device__ __forceinline__ void gn_partials(const float* v, float* vals) {
+  constexpr int D = 1 << LOGD;
+#pragma unroll
+  for (int g = 0; g < 32 / D; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const float r = __bfloat162float(__float2bfloat16_rn(v[g * D + j]));
+      s += r;
+      q = fmaf(r, r, q);
+    }
+    vals[2 * g] = s;
+    vals[2 * g + 1] = q;
+  }
+}
+// sum 16 per-lane values over the 32 lanes of the warp in 16 shuffles (recursive halving): afterwards lanes L and L^1
+// both hold the warp total of value index (bit4, bit3, bit2, bit1 of L)
+__device__ __forceinline__ float warp_reduce16(float* vals, int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 16 >> step, half = 8 >> step;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = up ? vals[i + half] : vals[i];
+      const float send = up ? vals[i] : vals[i + half];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return vals[0] + __shfl_xor_sync(0xffffffffu, vals[0], 1);
+}
+
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -235,6 +270,9 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tmem_ld32(taddr + ch * 32, r);
         tmem_wait_ld();
         const int col0 = nt * BLOCK_N + ch * 32;
+        float gv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gv[j] = 0.f;
         if (valid && col0 < p.Nout && !(p.dbg & 4)) {
           float v[32];
 #pragma unroll
@@ -273,6 +311,20 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.Nout) op[j] = __float2bfloat16_rn(v[j]);
+          }
+          if (p.gn_sums) {
+            if (p.gn_logD == 2) gn_partials<2>(v, gv);
+            else if (p.gn_logD == 3) gn_partials<3>(v, gv);
+            else gn_partials<4>(v, gv);
+          }
+        }
+        if (p.gn_sums && tc.valid && col0 < p.Nout) {  // warp-uniform: all 32 lanes take part in the shuffles
+          const float tot = warp_reduce16(gv, lane);
+          const int id = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          if ((lane & 1) == 0 && id < (64 >> p.gn_logD)) {
+            const int n_img = p.mode ? (int)(((long long)tc.n * p.W + tc.w0) / p.gn_rows_per_img) : tc.n;
+            const int group = (col0 >> p.gn_logD) + (id >> 1);
+            atomicAdd(p.gn_sums + ((long long)n_img * p.gn_G + group) * 2 + (id & 1), (double)tot);
           }
         }
       }

@@ -45,7 +45,20 @@ struct PairParams {
   long long out_sn, out_sh, out_sw;  // element strides of (n, h, w) in out / residual
   int Nout;
   uint32_t idesc;
+  // fused GroupNorm sums of the OUTPUT tensor (the next layer's GroupNorm): sum and sum of squares of the bf16-rounded
+  // outputs per (image, group) added to gn_sums[n][G][2]; every tile must lie inside one image
+  double* gn_sums;
+  int gn_G, gn_logD;       // groups, log2(channels per group) in {2, 3, 4}
+  int gn_rows_per_img;     // ROWS mode: rows of one image (a multiple of 128)
   int dbg;  // profiling aid (VCD_PAIR_DBG): 1 = epilogue only hand-shakes, 2 = MMA warp issues no MMAs, 4 = no stores
+};
+
+// request / result of the fused GroupNorm sums (host side)
+struct GnEpilogue {
+  double* sums;  // [N][groups][2], zeroed by the launcher when it fuses
+  int groups;
+  bool fused;    // set by the launcher: the kernel produced the sums
+  bool accumulate = false;  // add to sums already started by an earlier launch (phase convolutions): no zeroing
 };
 
 struct PairTap {

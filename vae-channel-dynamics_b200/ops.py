@@ -163,12 +163,29 @@ def pop_colsum(t: torch.Tensor):
 
 def clear_colsums() -> None:
     _COLSUMS.clear()
+    _GNSUMS.clear()
+
+
+# GroupNorm sums (sum, sum of squares per (image, group)) of a tensor, produced by the epilogue of the GEMM that wrote
+# it (vcd_conv2d_fprop gn_sums) and consumed by the GroupNorm that normalises it: no statistics pass over the tensor
+_GNSUMS = {}
+
+
+def push_gn_sums(t: torch.Tensor, sums: torch.Tensor, groups: int) -> None:
+    _GNSUMS[t.data_ptr()] = (t, sums, groups)
+
+
+def pop_gn_sums(t: torch.Tensor, groups: int):
+    e = _GNSUMS.pop(t.data_ptr(), None)
+    if e is None or e[0].shape != t.shape or e[2] != groups:
+        return None
+    return e[1]
 
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, packs: PackedWeights, stride: int, pad_t: int, pad_l: int,
-                out_hw, impl: int):
+                out_hw, impl: int, gn_groups: int = 0):
         x = _nhwc(x)
         N, H, W, Cin = x.shape
         Cout = weight.shape[0]
@@ -186,8 +203,11 @@ class _ConvFn(torch.autograd.Function):
             residual = _nhwc(residual)
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
         ws = _workspace("vcd_conv2d_fprop_ws_bytes", (N, H, W, Cin, Cout, KH, KW, stride), impl, x.device)
+        sums = torch.empty(N * gn_groups * 2, dtype=torch.float64, device=x.device) if gn_groups else None
         call("vcd_conv2d_fprop", _p(xs), _p(wf), _p(b32), _p(residual), _p(y), _p(ws), N, H, W, Cin, Cout, KH, KW, stride,
-             pad_t, pad_l, Ho, Wo, planes, impl, _st())
+             pad_t, pad_l, Ho, Wo, planes, impl, _p(sums), gn_groups, _st())
+        if sums is not None:
+            push_gn_sums(y, sums, gn_groups)
         ctx.save_for_backward(xs, weight, bias)
         ctx.packs = packs
         ctx.cfg = (N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl)
@@ -222,14 +242,15 @@ class _ConvFn(torch.autograd.Function):
             call("vcd_conv2d_wgrad", _p(xs), _p(dy), _p(dw), _p(db), _p(colsum), dtype_code(weight), _p(ws), N, H, W, Cin, Cout,
                  KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl, _st())
         dres = dy if ctx.has_res and ctx.needs_input_grad[3] else None
-        return dx, dw, db, dres, None, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None, None
 
 
-def conv2d(x, weight, bias, packs, stride=1, pad_t=1, pad_l=1, out_hw=None, residual=None, impl=None):
+def conv2d(x, weight, bias, packs, stride=1, pad_t=1, pad_l=1, out_hw=None, residual=None, impl=None, gn_groups=0):
+    """gn_groups > 0: the output feeds a GroupNorm of that many groups — its sums come out of the GEMM epilogue"""
     if out_hw is None:
         out_hw = (x.shape[1], x.shape[2])
     return _ConvFn.apply(x, weight, bias, residual, packs, stride, pad_t, pad_l, tuple(out_hw),
-                         _conv_impl if impl is None else impl)
+                         _conv_impl if impl is None else impl, gn_groups)
 
 
 class UpconvPackedWeights:
@@ -272,13 +293,16 @@ class _UpConvFn(torch.autograd.Function):
     GEMMs do 16/36 of the multiply-adds."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, packs: UpconvPackedWeights):
+    def forward(ctx, x, weight, bias, packs: UpconvPackedWeights, gn_groups: int = 0):
         x = _nhwc(x)
         N, H, W, Cin = x.shape
         Cout = weight.shape[0]
         wf, wd, b32 = packs.get(weight, bias)
         y = torch.empty((N, 2 * H, 2 * W, Cout), dtype=torch.bfloat16, device=x.device)
-        call("vcd_upconv2d_fprop", _p(x), _p(wf), _p(b32), _p(y), N, H, W, Cin, Cout, _st())
+        sums = torch.empty(N * gn_groups * 2, dtype=torch.float64, device=x.device) if gn_groups else None
+        call("vcd_upconv2d_fprop", _p(x), _p(wf), _p(b32), _p(y), N, H, W, Cin, Cout, _p(sums), gn_groups, _st())
+        if sums is not None:
+            push_gn_sums(y, sums, gn_groups)
         ctx.save_for_backward(x, weight, bias)
         ctx.packs = packs
         ctx.cfg = (N, H, W, Cin, Cout)
@@ -304,11 +328,11 @@ class _UpConvFn(torch.autograd.Function):
             ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
             call("vcd_upconv2d_wgrad", _p(x), _p(dyp), _p(dw), _p(db), _p(colsum), dtype_code(weight), _p(ws), N, H, W,
                  Cin, Cout, _st())
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def upconv2d(x, weight, bias, packs):
-    return _UpConvFn.apply(x, weight, bias, packs)
+def upconv2d(x, weight, bias, packs, gn_groups=0):
+    return _UpConvFn.apply(x, weight, bias, packs, gn_groups)
 
 
 # ------------------------------------------------------------------------------------------
@@ -326,9 +350,11 @@ class _GroupNormFn(torch.autograd.Function):
         x = _nhwc(x)
         N, C = x.shape[0], x.shape[-1]
         hw = x.numel() // (N * C)
-        sums = torch.empty(N * groups * 2, dtype=torch.float64, device=x.device)
-        call("vcd_gn_stats", _p(x), _p(sums), _p(None if slot_in is None else slot_in.raw),
-             0.0 if slot_in is None else slot_in.near_zero, N, hw, C, groups, _st())
+        sums = pop_gn_sums(x, groups) if slot_in is None else None
+        if sums is None:   # not produced by the epilogue of the GEMM that wrote x (or input statistics are tracked)
+            sums = torch.empty(N * groups * 2, dtype=torch.float64, device=x.device)
+            call("vcd_gn_stats", _p(x), _p(sums), _p(None if slot_in is None else slot_in.raw),
+                 0.0 if slot_in is None else slot_in.near_zero, N, hw, C, groups, _st())
         out = torch.empty_like(x)
         g, b = gamma.detach(), beta.detach()
         call("vcd_gn_apply_fwd", _p(x), _p(sums), _p(g), _p(b), dtype_code(g), _p(out),

@@ -65,6 +65,7 @@ class B200Conv2d(nn.Conv2d):
         super().__init__(cin, cout, k, stride=stride, padding=padding)
         self._packs = ops.PackedWeights()
         self._track_out: Optional[ops.TrackSlot] = None
+        self._gn_groups = 0   # > 0: the output feeds a GroupNorm of that many groups (sums fused into the epilogue)
 
     def forward(self, x, residual=None):
         xp = ops.to_nhwc(x)
@@ -75,7 +76,8 @@ class B200Conv2d(nn.Conv2d):
         else:  # Downsample2D: pad (0,1,0,1) then stride 2, no padding
             out_hw = (H // 2, W // 2)
         y = ops.conv2d(xp, self.weight, self.bias, self._packs, stride=s, pad_t=self.padding[0], pad_l=self.padding[1],
-                       out_hw=out_hw, residual=None if residual is None else _phys(residual))
+                       out_hw=out_hw, residual=None if residual is None else _phys(residual),
+                       gn_groups=0 if _hooked(self) else self._gn_groups)
         out = _logi(y)
         if self._track_out is not None:
             ops.chan_stats(out.detach(), self._track_out)
@@ -104,12 +106,14 @@ class B200Linear(nn.Linear):
     def __init__(self, cin, cout):
         super().__init__(cin, cout)
         self._packs = ops.PackedWeights()
+        self._gn_groups = 0
 
     def forward(self, x, residual=None):
         # x: physical [N, T, C]
         N, T, C = x.shape
         y = ops.conv2d(x.reshape(N, T, 1, C), self.weight, self.bias, self._packs, stride=1, pad_t=0, pad_l=0,
-                       out_hw=(T, 1), residual=None if residual is None else residual.reshape(N, T, 1, -1))
+                       out_hw=(T, 1), residual=None if residual is None else residual.reshape(N, T, 1, -1),
+                       gn_groups=self._gn_groups)
         return y.reshape(N, T, -1)
 
 
@@ -201,7 +205,7 @@ class Upsample2D(nn.Module):
         if _hooked(c) or c._track_out is not None or not ops.upconv_supported(c.in_channels, c.out_channels):
             # a hook on the conv must observe the upsampled tensor: materialise it
             return c(_logi(ops.upsample2x(_phys(x))))
-        return _logi(ops.upconv2d(_phys(x), c.weight, c.bias, self._up_packs))
+        return _logi(ops.upconv2d(_phys(x), c.weight, c.bias, self._up_packs, c._gn_groups))
 
 
 class DownEncoderBlock2D(nn.Module):
@@ -357,6 +361,27 @@ class B200AutoencoderKL(nn.Module):
         self.quant_conv = B200Conv2d(2 * lc, 2 * lc, 1)
         self.post_quant_conv = B200Conv2d(lc, lc, 1)
         self.output_dtype = torch.float32  # accelerate converts forward outputs to fp32 [upstream]
+        self._mark_groupnorm_producers(cfg["norm_num_groups"])
+
+    def _mark_groupnorm_producers(self, g: int):
+        """Every conv / linear whose output tensor is the input of a GroupNorm emits that GroupNorm's sums from its
+        GEMM epilogue (ops.conv2d gn_groups).  Block outputs feed the next block's norm1, the attention's group_norm
+        or conv_norm_out — except the last resnet of a block that ends in a Down/Upsample2D conv."""
+        def block(resnets, sampler):
+            for i, r in enumerate(resnets):
+                r.conv1._gn_groups = g
+                if sampler is None or i < len(resnets) - 1:
+                    r.conv2._gn_groups = g
+            if sampler is not None:
+                sampler.conv._gn_groups = g
+        for net in (self.encoder, self.decoder):
+            net.conv_in._gn_groups = g
+            blocks = net.down_blocks if net is self.encoder else net.up_blocks
+            for b in blocks:
+                samplers = b.downsamplers if net is self.encoder else b.upsamplers
+                block(b.resnets, None if samplers is None else samplers[0])
+            block(net.mid_block.resnets, None)
+            net.mid_block.attentions[0].to_out[0]._gn_groups = g
 
     # ---- diffusers-compatible surface ---------------------------------------------------
     @property
