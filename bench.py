@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--graph", action="store_true", help="replay forward+loss+backward from one CUDA graph (GraphedVAEStep); "
                     "default is the eager per-op path that unchanged train.py gets (DDP for N>1)")
     ap.add_argument("--quick", action="store_true", help="profiling aid: warm-up as given, no e2e/roofline/cpu legs")
+    ap.add_argument("--kernel-table", default="", help="profiling aid: after the timed run, trace 2 more steps with "
+                    "torch.profiler (CUPTI) and write the per-kernel device-time table to this file")
     return ap.parse_args()
 
 
@@ -403,6 +405,20 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     value = args.steps * B * world / (ms / 1e3)
     value_e2e = args.steps * B * world / (ms_e2e / 1e3)
+
+    if args.kernel_table and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(2):
+                train_step(resident[i % n_host])
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        with open(args.kernel_table, "w") as f:
+            f.write(f"2 steps, {tot / 2e3:.2f} ms of device time per step (torch.profiler / CUPTI, warm, in-pipeline)\n")
+            f.write(f"{'ms/step':>9} {'share':>6} {'n/step':>7}  kernel\n")
+            for e in rows[:45]:
+                f.write(f"{e.device_time_total / 2e3:9.3f} {100 * e.device_time_total / tot:5.1f}% {e.count / 2:7.1f}  {e.key[:110]}\n")
 
     roof = roof_hbm = cpu = None
     if rank == 0 and not args.no_roofline and not args.quick:

@@ -1,5 +1,5 @@
-"""Profiling aid: GroupNorm+SiLU forward/backward on one tensor shape (ncu captures / CUDA-event timing).
-  python tools/prof_gn.py --c 128 --h 512 --batch 8"""
+"""Profiling aid: GroupNorm+SiLU forward/backward on the model's tensor shapes (CUDA-event timing per kernel).
+  python tools/prof_gn.py [--batch 8] [--shapes 128,512 256,256 512,128 512,64]     (C,H)"""
 import argparse
 import os
 import sys
@@ -7,35 +7,53 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import vcd_b200
+from vcd_b200.ops import _p, _st, call, dtype_code
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--c", type=int, default=128)
-ap.add_argument("--h", type=int, default=512)
 ap.add_argument("--batch", type=int, default=8)
-ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--shapes", nargs="*", default=["128,512", "256,512", "256,256", "512,256", "512,128", "512,64"])
 a = ap.parse_args()
-ops = vcd_b200.ops
-B, h, C = a.batch, a.h, a.c
-xs = [torch.randn(B, h, h, C, device="cuda").to(torch.bfloat16).requires_grad_() for _ in range(3)]
-g = torch.randn(B, h, h, C, device="cuda").to(torch.bfloat16)
-gamma = torch.ones(C, device="cuda", dtype=torch.bfloat16, requires_grad=True)
-beta = torch.zeros(C, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+B = a.batch
+for sh in a.shapes:
+    C, h = (int(v) for v in sh.split(","))
+    n = B * h * h * C
+    nbuf = min(6, max(2, int(300e6 // (n * 2)) + 1))
+    xs = [torch.randn(B, h, h, C, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+    gs = [torch.randn(B, h, h, C, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+    rs = [torch.randn(B, h, h, C, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+    out = torch.empty_like(xs[0])
+    gamma = torch.ones(C, device="cuda", dtype=torch.bfloat16)
+    beta = torch.zeros(C, device="cuda", dtype=torch.bfloat16)
+    sums = torch.empty(B * 32 * 2, dtype=torch.float64, device="cuda")
+    dsdb = torch.empty(B * C * 2, dtype=torch.float32, device="cuda")
+    colsum = torch.empty(C, dtype=torch.float32, device="cuda")
+    pdt = dtype_code(gamma)
+    hw = h * h
+    call("vcd_gn_stats", _p(xs[0]), _p(sums), None, 0.0, B, hw, C, 32, _st())
 
-
-def run(i):
-    y, xid = ops.group_norm(xs[i % 3], gamma, beta, 32, 1e-6, True, None, None, True)
-    torch.autograd.backward([y, xid], [g, g])
-
-
-for i in range(2):
-    run(i)
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-torch.cuda.synchronize()
-ev[0].record()
-for i in range(a.iters):
-    run(i)
-ev[1].record()
-torch.cuda.synchronize()
-ms = ev[0].elapsed_time(ev[1]) / a.iters
-n = B * h * h * C
-print(f"GN+SiLU fwd+bwd C={C} @{h} B={B}: {ms:.3f} ms; algorithmic (4+8 B/elem incl. skip grad) {12 * n / ms / 1e6:.0f} GB/s")
+    fns = {
+        "stats": (lambda i: call("vcd_gn_stats", _p(xs[i % nbuf]), _p(sums), None, 0.0, B, hw, C, 32, _st()), 2),
+        "apply": (lambda i: call("vcd_gn_apply_fwd", _p(xs[i % nbuf]), _p(sums), _p(gamma), _p(beta), pdt, _p(out), None, 0.0,
+                                 1e-6, 1, B, hw, C, 32, _st()), 4),
+        "bwd_reduce": (lambda i: call("vcd_gn_bwd_reduce", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(sums), _p(gamma), _p(beta),
+                                      pdt, _p(dsdb), 1e-6, 1, B, hw, C, 32, _st()), 4),
+        "bwd_apply": (lambda i: call("vcd_gn_bwd_apply", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(sums), _p(gamma), _p(beta), pdt,
+                                     _p(dsdb), _p(out), None, _p(colsum), 1e-6, 1, B, hw, C, 32, _st()), 6),
+        "bwd_apply+res": (lambda i: call("vcd_gn_bwd_apply", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(sums), _p(gamma), _p(beta),
+                                         pdt, _p(dsdb), _p(out), _p(rs[i % nbuf]), _p(colsum), 1e-6, 1, B, hw, C, 32, _st()), 8),
+    }
+    line = []
+    for name, (fn, bpe) in fns.items():
+        for i in range(2):
+            fn(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(a.iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.iters
+        line.append(f"{name} {ms * 1e3:6.1f} us {bpe * n / ms / 1e6:5.0f} GB/s")
+    print(f"C={C:4d} @{h:4d} B={B}: " + " | ".join(line), flush=True)

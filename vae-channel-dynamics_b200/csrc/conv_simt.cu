@@ -220,13 +220,67 @@ __global__ void __launch_bounds__(128) wgrad_small_out_kernel(const bf16* __rest
 }
 
 // db[c] = sum over pixels dy[p][c]
+// C % 8 == 0: thread (pl, v) owns 8 channels (one 16-byte load per pixel) and walks pixels pl, pl+PL, ... of the block's
+// range; partials meet in shared memory, one atomicAdd per (block, channel).
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const bf16* __restrict__ dy, float* __restrict__ out, int64_t pixels,
+                                                         int C, int64_t chunk) {
+  extern __shared__ float red[];  // [8][PL][V]
+  const int V = C >> 3, PL = 256 / V;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V;
+  const int64_t p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, pixels);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const bf16* base = dy + v * 8;
+  int64_t p = p0 + pl;
+  for (; p + 3 * (int64_t)PL < p1; p += 4 * (int64_t)PL) {
+    bf16x8 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = ld8(base + (p + (int64_t)u * PL) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(t[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+  for (; p < p1; p += PL) {
+    float f[8];
+    unpack8(ld8(base + p * C), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+  if (pl < PL) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[(j * PL + pl) * V + v] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int cv = c >> 3, j = c & 7;
+    float t = 0.f;
+    for (int q = 0; q < PL; ++q) t += red[(j * PL + q) * V + cv];
+    atomicAdd(&out[c], t);
+  }
+}
+// any C (the 3 / 4 / 8-channel tensors): one pixel per thread and iteration, warp-shuffle sum per channel
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, int64_t pixels,
                                                      int C, int64_t chunk) {
   const int64_t p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, pixels);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int64_t p = p0; p < p1; ++p) acc += __bfloat162float(dy[p * C + c]);
-    atomicAdd(&out[c], acc);
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += 256) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < C) acc[j] += __bfloat162float(dy[p * C + c0 + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = warp_sum(acc[j]);
+      if ((threadIdx.x & 31) == 0 && c0 + j < C) atomicAdd(&out[c0 + j], t);
+    }
   }
 }
 
@@ -343,7 +397,11 @@ int conv_bias_grad(const void* dy, float* out, int64_t pixels, int C, cudaStream
   int64_t chunks = (int64_t)vcd_num_sms() * 4;
   int64_t chunk = ceil_div64(pixels, chunks);
   if (chunk < 32) chunk = 32;
-  colsum_kernel<<<(unsigned)ceil_div64(pixels, chunk), 256, 0, st>>>((const bf16*)dy, out, pixels, C, chunk);
+  if (C % 8 == 0 && 256 % (C / 8) == 0 && C / 8 <= 256)
+    colsum_vec_kernel<<<(unsigned)ceil_div64(pixels, chunk), 256, 8 * 256 * sizeof(float), st>>>((const bf16*)dy, out, pixels,
+                                                                                                  C, chunk);
+  else
+    colsum_kernel<<<(unsigned)ceil_div64(pixels, chunk), 256, 0, st>>>((const bf16*)dy, out, pixels, C, chunk);
   VCD_LAUNCH_CHECK();
   return 0;
 }

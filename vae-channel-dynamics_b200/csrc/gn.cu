@@ -13,22 +13,19 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kIters = 64;  // pixels per thread per block
-
 constexpr int kUnroll = 4;
 
 struct Map {
   int V, PL, v, pl, c0;
   int64_t p_begin, p_end;
 };
-__device__ __forceinline__ Map make_map(int C, int HW) {
+__device__ __forceinline__ Map make_map(int C, int HW, int ppb) {  // ppb = pixels per block (host: gn_launch_shape)
   Map m;
   m.V = C >> 3;
   m.PL = kThreads / m.V;
   m.v = threadIdx.x % m.V;
   m.pl = threadIdx.x / m.V;
   m.c0 = m.v * 8;
-  int64_t ppb = (int64_t)m.PL * kIters;
   m.p_begin = (int64_t)blockIdx.x * ppb;
   m.p_end = min(m.p_begin + ppb, (int64_t)HW);
   return m;
@@ -78,11 +75,11 @@ constexpr int kMaxGroups = 64;
 template <bool STATS>
 __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ sums,
                                                             float* __restrict__ cstats, float near_zero, int HW,
-                                                            int C, int G) {
+                                                            int C, int G, int ppb) {
   extern __shared__ float red[];  // [K][8][PL][V] with K = 2 (5 when STATS), then [C][2] channel sums
   constexpr int K = STATS ? 5 : 2;
   const int n = blockIdx.y;
-  Map m = make_map(C, HW);
+  Map m = make_map(C, HW, ppb);
   float acc[K][8];
 #pragma unroll
   for (int k = 0; k < K; ++k)
@@ -147,10 +144,10 @@ template <bool STATS>
 __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ sums,
                                                             const void* __restrict__ gamma, const void* __restrict__ beta,
                                                             int pdt, bf16* __restrict__ out, float* __restrict__ cstats,
-                                                            float near_zero, float eps, int act, int HW, int C, int G) {
+                                                            float near_zero, float eps, int act, int HW, int C, int G, int ppb) {
   extern __shared__ float sm[];  // [5][8][PL][V] when STATS
   const int n = blockIdx.y;
-  Map m = make_map(C, HW);
+  Map m = make_map(C, HW, ppb);
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
@@ -212,15 +209,15 @@ __global__ void __launch_bounds__(kThreads) gn_apply_kernel(const bf16* __restri
 }
 
 // ---------------------------------------------------------------- backward pass 1: ds/db per (n, c)
-__global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
+__global__ void __launch_bounds__(kThreads, 2) gn_bwd_reduce_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
                                                                  const double* __restrict__ sums,
                                                                  const void* __restrict__ gamma,
                                                                  const void* __restrict__ beta, int pdt,
                                                                  float* __restrict__ dsdb, float eps, int act, int HW,
-                                                                 int C, int G) {
+                                                                 int C, int G, int ppb) {
   extern __shared__ float sm[];  // [2][8][PL][V]
   const int n = blockIdx.y;
-  Map m = make_map(C, HW);
+  Map m = make_map(C, HW, ppb);
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
@@ -234,19 +231,24 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const bf16* __r
     ds[j] = db[j] = 0.f;
   }
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
-    bf16x8 vx[kUnroll], vg[kUnroll];
+  // register double buffer: the loads of the next stage are in flight while this stage is reduced
+  constexpr int U = 2;
+  const int64_t S = (int64_t)U * m.PL;
+  bf16x8 bx[2][U], bg[2][U];
+  auto load = [&](int64_t q, bf16x8* vx, bf16x8* vg) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p < m.p_end) {
-        vx[u] = ld8(x + base + p * C);
-        vg[u] = ld8(dout + base + p * C);
+    for (int u = 0; u < U; ++u) {
+      const int64_t pp = q + (int64_t)u * m.PL;
+      if (pp < m.p_end) {
+        vx[u] = ld8(x + base + pp * C);
+        vg[u] = ld8(dout + base + pp * C);
       }
     }
+  };
+  auto compute = [&](int64_t q, const bf16x8* vx, const bf16x8* vg) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (p0 + (int64_t)u * m.PL >= m.p_end) break;
+    for (int u = 0; u < U; ++u) {
+      if (q + (int64_t)u * m.PL >= m.p_end) break;
       float f[8], g[8];
       unpack8(vx[u], f);
       unpack8(vg[u], g);
@@ -254,9 +256,23 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_reduce_kernel(const bf16* __r
       for (int j = 0; j < 8; ++j) {
         float gg = g[j];
         if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
-        ds[j] += gg * f[j];
+        ds[j] = fmaf(gg, f[j], ds[j]);
         db[j] += gg;
       }
+    }
+  };
+  int64_t pq = m.p_begin + m.pl;
+  if (pq < m.p_end) {
+    load(pq, bx[0], bg[0]);
+    while (true) {
+      if (pq + S < m.p_end) load(pq + S, bx[1], bg[1]);
+      compute(pq, bx[0], bg[0]);
+      pq += S;
+      if (pq >= m.p_end) break;
+      if (pq + S < m.p_end) load(pq + S, bx[0], bg[0]);
+      compute(pq, bx[1], bg[1]);
+      pq += S;
+      if (pq >= m.p_end) break;
     }
   }
   float acc[2][8];
@@ -279,11 +295,11 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_kernel(const bf16* _
                                                                 const float* __restrict__ dsdb, bf16* __restrict__ dx,
                                                                 const bf16* __restrict__ dres,
                                                                 float* __restrict__ colsum, float eps, int act, int HW,
-                                                                int C, int G) {
+                                                                int C, int G, int ppb) {
   extern __shared__ float sm[];  // [1][8][PL][V] when colsum
   constexpr int kU = 2;          // fewer pixels in flight than the other passes: three streams per pixel
   const int n = blockIdx.y;
-  Map m = make_map(C, HW);
+  Map m = make_map(C, HW, ppb);
   float cs[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) cs[j] = 0.f;
@@ -318,21 +334,25 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_kernel(const bf16* _
     c3[j] = pc3;
   }
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kU * m.PL) {
-    bf16x8 vx[kU], vg[kU], vr[kU];
+  // register double buffer: the loads of the next stage are in flight while this stage is computed and stored
+  const int64_t S = (int64_t)kU * m.PL;
+  bf16x8 bx[2][kU], bg[2][kU], br[2][kU];
+  auto load = [&](int64_t q, bf16x8* vx, bf16x8* vg, bf16x8* vr) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p < m.p_end) {
-        vx[u] = ld8(x + base + p * C);
-        vg[u] = ld8(dout + base + p * C);
-        if (HAS_RES) vr[u] = ld8(dres + base + p * C);
+      const int64_t pp = q + (int64_t)u * m.PL;
+      if (pp < m.p_end) {
+        vx[u] = ld8(x + base + pp * C);
+        vg[u] = ld8(dout + base + pp * C);
+        if (HAS_RES) vr[u] = ld8(dres + base + pp * C);
       }
     }
+  };
+  auto compute = [&](int64_t q, const bf16x8* vx, const bf16x8* vg, const bf16x8* vr) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p >= m.p_end) break;
+      const int64_t pp = q + (int64_t)u * m.PL;
+      if (pp >= m.p_end) break;
       float f[8], g[8], r[8];
       unpack8(vx[u], f);
       unpack8(vg[u], g);
@@ -346,7 +366,21 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_kernel(const bf16* _
         g[j] = d;
         cs[j] += d;
       }
-      st8(dx + base + p * C, pack8(g));
+      st8(dx + base + pp * C, pack8(g));
+    }
+  };
+  int64_t pq = m.p_begin + m.pl;
+  if (pq < m.p_end) {
+    load(pq, bx[0], bg[0], br[0]);
+    while (true) {
+      if (pq + S < m.p_end) load(pq + S, bx[1], bg[1], br[1]);
+      compute(pq, bx[0], bg[0], br[0]);
+      pq += S;
+      if (pq >= m.p_end) break;
+      if (pq + S < m.p_end) load(pq + S, bx[0], bg[0], br[0]);
+      compute(pq, bx[1], bg[1], br[1]);
+      pq += S;
+      if (pq >= m.p_end) break;
     }
   }
   if (colsum) {
@@ -392,9 +426,27 @@ int check_shape(int C, int G) {
   }
   return 0;
 }
-dim3 gn_grid(int N, int HW, int C) {
-  int PL = kThreads / (C / 8);
-  return dim3((unsigned)ceil_div64(HW, (int64_t)PL * kIters), (unsigned)N);
+// Launch shape: blocks of `ppb` pixels inside one image.  The grid is sized to `bps` resident blocks per SM times a
+// whole number of waves (no ragged last wave), with at most ~2048 pixels-iterations per thread block so that small
+// tensors still spread over all SMs.
+struct GnShape {
+  dim3 grid;
+  int ppb;
+};
+GnShape gn_launch_shape(int N, int HW, int C, int bps) {
+  const int PL = kThreads / (C / 8);
+  const int64_t resident = (int64_t)vcd_num_sms() * bps;
+  int64_t waves = 1;
+  // at most 64 loop iterations (pixels per thread) per block
+  while (ceil_div64((int64_t)N * HW, resident * waves) > (int64_t)PL * 64) ++waves;
+  int64_t per_img = (resident * waves) / N;
+  if (per_img < 1) per_img = 1;
+  int64_t ppb = ceil_div64(HW, per_img);
+  ppb = ceil_div64(ppb, PL) * PL;
+  GnShape r;
+  r.ppb = (int)ppb;
+  r.grid = dim3((unsigned)ceil_div64(HW, ppb), (unsigned)N);
+  return r;
 }
 
 }  // namespace
@@ -404,12 +456,13 @@ extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, f
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
   VCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * G, st));
+  const GnShape sh = gn_launch_shape(N, HW, C, 4);
   if (chan_stats_in)
-    gn_stats_kernel<true><<<gn_grid(N, HW, C), kThreads, (5 * 8 * kThreads + 2 * C) * sizeof(float), st>>>((const bf16*)x, sums, chan_stats_in,
-                                                                                     near_zero, HW, C, G);
+    gn_stats_kernel<true><<<sh.grid, kThreads, (5 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
+        (const bf16*)x, sums, chan_stats_in, near_zero, HW, C, G, sh.ppb);
   else
-    gn_stats_kernel<false><<<gn_grid(N, HW, C), kThreads, (2 * 8 * kThreads + 2 * C) * sizeof(float), st>>>((const bf16*)x, sums, nullptr,
-                                                                                      near_zero, HW, C, G);
+    gn_stats_kernel<false><<<sh.grid, kThreads, (2 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
+        (const bf16*)x, sums, nullptr, near_zero, HW, C, G, sh.ppb);
   VCD_LAUNCH_CHECK();
   return 0;
 }
@@ -419,12 +472,13 @@ extern "C" int vcd_gn_apply_fwd(const void* x, const double* sums, const void* g
                                 int HW, int C, int G, vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
+  const GnShape sh = gn_launch_shape(N, HW, C, 3);
   if (chan_stats_out)
-    gn_apply_kernel<true><<<gn_grid(N, HW, C), kThreads, 5 * 8 * kThreads * sizeof(float), st>>>(
-        (const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, chan_stats_out, near_zero, eps, act_silu, HW, C, G);
+    gn_apply_kernel<true><<<sh.grid, kThreads, 5 * 8 * kThreads * sizeof(float), st>>>(
+        (const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, chan_stats_out, near_zero, eps, act_silu, HW, C, G, sh.ppb);
   else
-    gn_apply_kernel<false><<<gn_grid(N, HW, C), kThreads, 0, st>>>((const bf16*)x, sums, gamma, beta, param_dtype,
-                                                                   (bf16*)out, nullptr, near_zero, eps, act_silu, HW, C, G);
+    gn_apply_kernel<false><<<sh.grid, kThreads, 0, st>>>((const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, nullptr,
+                                                         near_zero, eps, act_silu, HW, C, G, sh.ppb);
   VCD_LAUNCH_CHECK();
   return 0;
 }
@@ -435,8 +489,9 @@ extern "C" int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* 
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
   VCD_CUDA(cudaMemsetAsync(dsdb, 0, sizeof(float) * 2 * N * C, st));
-  gn_bwd_reduce_kernel<<<gn_grid(N, HW, C), kThreads, 2 * 8 * kThreads * sizeof(float), st>>>(
-      (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, eps, act_silu, HW, C, G);
+  const GnShape sh = gn_launch_shape(N, HW, C, 2);
+  gn_bwd_reduce_kernel<<<sh.grid, kThreads, 2 * 8 * kThreads * sizeof(float), st>>>(
+      (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, eps, act_silu, HW, C, G, sh.ppb);
   VCD_LAUNCH_CHECK();
   return 0;
 }
@@ -447,14 +502,15 @@ extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* s
   if (check_shape(C, G)) return -1;
   if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, as_stream(stream)));
   const size_t smem = dx_colsum ? 8 * kThreads * sizeof(float) : 0;
+  const GnShape sh = gn_launch_shape(N, HW, C, 2);
   if (dres)
-    gn_bwd_apply_kernel<true><<<gn_grid(N, HW, C), kThreads, smem, as_stream(stream)>>>(
+    gn_bwd_apply_kernel<true><<<sh.grid, kThreads, smem, as_stream(stream)>>>(
         (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum,
-        eps, act_silu, HW, C, G);
+        eps, act_silu, HW, C, G, sh.ppb);
   else
-    gn_bwd_apply_kernel<false><<<gn_grid(N, HW, C), kThreads, smem, as_stream(stream)>>>(
+    gn_bwd_apply_kernel<false><<<sh.grid, kThreads, smem, as_stream(stream)>>>(
         (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, nullptr, dx_colsum, eps,
-        act_silu, HW, C, G);
+        act_silu, HW, C, G, sh.ppb);
   VCD_LAUNCH_CHECK();
   return 0;
 }
