@@ -71,6 +71,18 @@ int64_t vcd_conv2d_dgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH
 int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void* w_dgrad, void* dx, void* ws,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
                      int Ho, int Wo, int dx_planes, int impl, vcd_stream_t stream);
+/* dgrad of a 3x3 stride-1 conv whose INPUT was act(GroupNorm(gn_x)) (ResnetBlock2D norm1->conv1, norm2->conv2), fused
+ * with the first half of that GroupNorm's backward: instead of dL/d(input) the call stores
+ *     g = dL/d(input) * SiLU'(a*gn_x + b)        (gn_act = 0: g = dL/d(input))
+ * in g_out, and accumulates gn_dsdb[n][c] = (sum_p g*gn_x, sum_p g) — exactly what vcd_gn_bwd_reduce computes — in the
+ * GEMM epilogue.  The GroupNorm backward then is vcd_gn_bwd_apply(x, g, ..., act_silu = 0) + vcd_gn_param_grad: one
+ * pass over the tensors instead of two.  gn_ab_ws: fp32 [N][Cin][2] scratch.  Only shapes for which
+ * vcd_conv2d_dgrad_gn_supported() returns 1. */
+int vcd_conv2d_dgrad_gn_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
+int vcd_conv2d_dgrad_gn(const void* dy, const void* w_dgrad, void* g_out, int N, int H, int W, int Cin, int Cout,
+                        int KH, int KW, int pad_t, int pad_l, const void* gn_x, const double* gn_sums,
+                        const void* gn_gamma, const void* gn_beta, int param_dtype, int gn_groups, float gn_eps,
+                        int gn_act, float* gn_dsdb, float* gn_ab_ws, vcd_stream_t stream);
 /* dw (OIHW, `dtype`) and db ([Cout], `dtype`, may be NULL).  ws: workspace of vcd_conv2d_wgrad_ws_bytes()
  * bytes (zeroed by the call).  db_colsum (fp32 [Cout], may be NULL): column sums of dy already produced by
  * the kernel that wrote dy (vcd_gn_bwd_apply), which saves the bias-gradient pass over dy. */

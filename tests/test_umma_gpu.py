@@ -208,3 +208,45 @@ def test_upconv_epilogue_groupnorm_sums(vcd):
     yf = y.double().reshape(2, 32 * 32, 32, 8)
     ref = torch.stack([yf.sum(dim=(1, 3)), (yf * yf).sum(dim=(1, 3))], dim=-1).reshape(-1)
     assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-3), float((sums - ref).abs().max())
+
+
+@pytest.mark.parametrize("N,H,W,C,cout,split", [(2, 32, 16, 256, 128, False), (3, 16, 8, 256, 512, True),
+                                                (1, 40, 24, 512, 256, True), (2, 16, 16, 128, 256, False)])
+def test_groupnorm_backward_fused_into_conv_dgrad(vcd, N, H, W, C, cout, split):
+    """GroupNorm+SiLU -> conv3x3: with sole_consumer_is_conv the conv's dgrad epilogue applies SiLU' and reduces the
+    GroupNorm backward sums (vcd_conv2d_dgrad_gn); gradients must match the torch fp32 chain and the unfused path."""
+    ops = vcd.ops
+    x = bf16_round(torch.randn(N, C, H, W, device="cuda") * 1.5 + 0.3)
+    gamma = bf16_round(torch.rand(C, device="cuda") + 0.5)
+    beta = bf16_round(torch.randn(C, device="cuda") * 0.2)
+    w = bf16_round(torch.randn(cout, C, 3, 3, device="cuda") / math.sqrt(9 * C))
+    b = torch.randn(cout, device="cuda")
+    g = bf16_round(torch.randn(N, cout, H, W, device="cuda"))
+    gskip = bf16_round(torch.randn(N, C, H, W, device="cuda"))
+    xr, gr, br, wr = (t.clone().requires_grad_() for t in (x, gamma, beta, w))
+    h = F.silu(F.group_norm(xr, 32, gr, br, 1e-6))
+    ref = F.conv2d(h, wr, b, padding=1)
+    (ref * g).sum().backward() if not split else ((ref * g).sum() + (xr * gskip).sum()).backward()
+
+    def run(fuse):
+        ops.clear_colsums()
+        xp = nhwc(x).requires_grad_()
+        gp, bp, wp = gamma.clone().requires_grad_(), beta.clone().requires_grad_(), w.clone().requires_grad_()
+        out = ops.group_norm(xp, gp, bp, 32, 1e-6, True, None, None, split, fuse)
+        hh, xid = out if split else (out, None)
+        y = ops.conv2d(hh, wp, b, ops.PackedWeights())
+        loss = (y.float() * nhwc(g).float()).sum()
+        if split:
+            loss = loss + (xid.float() * nhwc(gskip).float()).sum()
+        loss.backward()
+        return y, xp.grad, gp.grad, bp.grad, wp.grad
+
+    lib = vcd._lib.lib()
+    y1, dx1, dg1, db1, dw1 = run(True)
+    assert not ops._GN_BWD and not ops._GN_FWD          # both hand-offs were consumed (C = 128: fusion declined)
+    y0, dx0, dg0, db0, dw0 = run(False)
+    assert rel_err(nchw(y1), ref) < TOL
+    for a, r, name in ((nchw(dx1), xr.grad, "dx"), (dg1, gr.grad, "dgamma"), (db1, br.grad, "dbeta"), (dw1, wr.grad, "dw")):
+        assert rel_err(a, r) < 2e-2, name
+    for a, r, name in ((dx1, dx0, "dx"), (dg1, dg0, "dgamma"), (db1, db0, "dbeta")):
+        assert rel_err(a, r) < 1e-2, name + " fused vs unfused"

@@ -48,9 +48,24 @@ for sh in a.shapes:
         call("vcd_conv2d_wgrad", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(dw), _p(db), _p(colsum), dtype_code(w), _p(ws), B, h, h,
              ci, co, k, k, 1, pad, pad, h, h, 0, 0, _st())
 
+    # dgrad with the fused GroupNorm backward prologue (3x3 only)
+    gsums = torch.empty(B * 32 * 2, dtype=torch.float64, device="cuda")
+    call("vcd_gn_stats", _p(xs[0]), _p(gsums), None, 0.0, B, h * h, ci, 32, _st())
+    gamma = torch.ones(ci, device="cuda", dtype=torch.bfloat16)
+    beta = torch.zeros(ci, device="cuda", dtype=torch.bfloat16)
+    dsdb = torch.empty(B * ci * 2, dtype=torch.float32, device="cuda")
+    ab = torch.empty(B * ci * 2, dtype=torch.float32, device="cuda")
+
+    def dgrad_gn(i):
+        call("vcd_conv2d_dgrad_gn", _p(gs[i % nbuf]), _p(wd), _p(dx), B, h, h, ci, co, k, k, pad, pad, _p(xs[i % nbuf]),
+             _p(gsums), _p(gamma), _p(beta), dtype_code(gamma), 32, 1e-6, 1, _p(dsdb), _p(ab), _st())
+
     fl = 2.0 * B * h * h * co * ci * k * k
     out = []
-    for name, fn in (("fprop", fprop), ("dgrad", dgrad), ("wgrad", wgrad)):
+    passes = [("fprop", fprop), ("dgrad", dgrad), ("wgrad", wgrad)]
+    if k == 3 and lib.vcd_conv2d_dgrad_gn_supported(B, h, h, ci, co, k, k, 1):
+        passes.append(("dgrad+gn", dgrad_gn))
+    for name, fn in passes:
         for i in range(2):
             fn(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

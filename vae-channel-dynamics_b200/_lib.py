@@ -23,6 +23,8 @@ SIGNATURES = {
     "vcd_conv2d_fprop": (_i, [_p] * 6 + [_i] * 14 + [_p, _i, _p]),
     "vcd_conv2d_dgrad_ws_bytes": (_i64, [_i] * 8),
     "vcd_conv2d_dgrad": (_i, [_p] * 5 + [_i] * 14 + [_p]),
+    "vcd_conv2d_dgrad_gn_supported": (_i, [_i] * 8),
+    "vcd_conv2d_dgrad_gn": (_i, [_p] * 3 + [_i] * 9 + [_p] * 4 + [_i, _i, _f, _i, _p, _p, _p]),
     "vcd_conv2d_wgrad_ws_bytes": (_i64, [_i] * 8),
     "vcd_conv2d_wgrad": (_i, [_p] * 5 + [_i] + [_p] + [_i] * 14 + [_p]),
     "vcd_pack_upconv_weight": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),

@@ -101,7 +101,8 @@ int attach_gn(PairParams& p, GnEpilogue* gn, int n_images, int Nout, int rows_pe
 // implicit-GEMM convolution with halo reuse: returns 1 when launched, 0 when the shape is not eligible, < 0 on error
 int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, int Ht, const PairTap* taps, int ntaps,
                   const void* wpack, int wrows, const float* bias, const void* residual, void* out, long long sn,
-                  long long sh, long long sw, int Nout, cudaStream_t st, GnEpilogue* gn = nullptr) {
+                  long long sh, long long sw, int Nout, cudaStream_t st, GnEpilogue* gn = nullptr,
+                  const GnBwdPrologue* gnb = nullptr) {
   if (!pair_enabled() || C % 64 != 0) return 0;
   PairParams p;
   memset(&p, 0, sizeof(p));
@@ -117,6 +118,11 @@ int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, 
   CUtensorMap mA, mB;
   int rc;
   if ((rc = attach_gn(p, gn, N, Nout, 0, st))) return rc;
+  if (gnb) {
+    VCD_CHECK_ARG(Nout <= 512 && Nout % 32 == 0, "fused GroupNorm backward: channels must be a multiple of 32, <= 512");
+    p.gnb_x = (const bf16*)gnb->x; p.gnb_ab = gnb->ab; p.gnb_dsdb = gnb->dsdb; p.gnb_act = gnb->act;
+    VCD_CUDA(cudaMemsetAsync(gnb->dsdb, 0, sizeof(float) * 2 * N * Nout, st));
+  }
   if ((rc = make_act_map(&mA, act, C, Wa, Ha, P, N, 64, p.box_w, box_h, 1))) return rc;
   if ((rc = make_act_map(&mB, wpack, C, wrows, 1, 1, 1, 64, bn / 2, 1, 1))) return rc;
   if ((rc = pair_launch(mA, mB, p, bn, st))) return rc;
@@ -803,6 +809,35 @@ extern "C" int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void*
   if (path == 3) return narrow_conv(dy, w_dgrad, nullptr, dx, N, H, W, Cout, Cin, KH, KW, pad_t, pad_l, -1, st);
   if (path == 4) return patch_gemm(dy, w_dgrad, nullptr, dx, ws, N, H, W, Cout, Cin, KH, KW, pad_t, pad_l, -1, st);
   return simt_conv_dgrad(dy, w_dgrad, dx, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, st);
+}
+
+// ---- dgrad with the fused GroupNorm backward prologue (see include/vcd.h)
+extern "C" int vcd_conv2d_dgrad_gn_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
+  (void)N;
+  // Cin >= 256: with 128 channels the GEMM item (K = 1152) is too short to hide the ~900-instruction fused epilogue —
+  // measured on B200: +348 us on the dgrad against 210 us for the stand-alone vcd_gn_bwd_reduce (tools/prof_conv2.py)
+  return (pair_enabled() && umma_shape_ok(Cin, Cout, KH, KW, stride) && KH == 3 && KW == 3 && stride == 1 && W >= 8 &&
+          H >= 16 && Cin <= 512 && Cin >= 256 && Cin % 32 == 0) ? 1 : 0;
+}
+extern "C" int vcd_conv2d_dgrad_gn(const void* dy, const void* w_dgrad, void* g_out, int N, int H, int W, int Cin, int Cout,
+                                   int KH, int KW, int pad_t, int pad_l, const void* gn_x, const double* gn_sums,
+                                   const void* gn_gamma, const void* gn_beta, int param_dtype, int gn_groups, float gn_eps,
+                                   int gn_act, float* gn_dsdb, float* gn_ab_ws, vcd_stream_t stream) {
+  VCD_CHECK_ARG(dy && w_dgrad && g_out && gn_x && gn_sums && gn_gamma && gn_beta && gn_dsdb && gn_ab_ws,
+                "conv dgrad+GN: null pointer");
+  VCD_CHECK_ARG(vcd_conv2d_dgrad_gn_supported(N, H, W, Cin, Cout, KH, KW, 1), "conv dgrad+GN: shape not supported");
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if ((rc = gn_make_ab(gn_sums, gn_gamma, gn_beta, param_dtype, gn_eps, N, H * W, Cin, gn_groups, gn_ab_ws, st))) return rc;
+  GnBwdPrologue gnb{gn_x, gn_ab_ws, gn_dsdb, gn_act};
+  PairTap taps[9];
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) taps[kh * KW + kw] = PairTap{0, pad_t - kh, pad_l - kw, (kh * KW + kw) * Cin};
+  rc = try_pair_halo(dy, Cout, W, H, 1, N, W, H, taps, KH * KW, w_dgrad, KH * KW * Cin, nullptr, nullptr, g_out,
+                     (long long)H * W * Cin, (long long)W * Cin, Cin, Cin, st, nullptr, &gnb);
+  if (rc < 0) return rc;
+  VCD_CHECK_ARG(rc == 1, "conv dgrad+GN: the pair kernel did not take the shape");
+  return 0;
 }
 
 // workspace: fp32 [tap][Cout][Cin] + [Cout]  (+ small-channel path: bf16 patch [px][Np] + fp32 D [big][Np])

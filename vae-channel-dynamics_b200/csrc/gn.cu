@@ -414,6 +414,22 @@ __global__ void gn_param_grad_kernel(const double* __restrict__ sums, const floa
   store_param(dbeta, pdt, c, dbv);
 }
 
+// ab[n][c] = (a, b) with y = a * x + b the affine GroupNorm of image n, channel c (used by the conv dgrad epilogue that
+// applies SiLU' and reduces the GroupNorm backward sums, umma_pair.cu)
+__global__ void gn_ab_kernel(const double* __restrict__ sums, const void* __restrict__ gamma, const void* __restrict__ beta,
+                             int pdt, float eps, int N, int HW, int C, int G, float* __restrict__ ab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C, D = C / G, g = c / D;
+  const double cnt = (double)D * (double)HW;
+  const double mu = sums[((int64_t)n * G + g) * 2] / cnt;
+  double var = sums[((int64_t)n * G + g) * 2 + 1] / cnt - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float a = (float)(1.0 / sqrt(var + (double)eps)) * load_param(gamma, pdt, c);
+  ab[2 * i] = a;
+  ab[2 * i + 1] = load_param(beta, pdt, c) - (float)mu * a;
+}
+
 int check_shape(int C, int G) {
   int V = C / 8;
   if (C % 8 != 0 || V < 1 || V > kThreads || (kThreads % V) != 0) {
@@ -450,6 +466,14 @@ GnShape gn_launch_shape(int N, int HW, int C, int bps) {
 }
 
 }  // namespace
+
+int gn_make_ab(const double* sums, const void* gamma, const void* beta, int pdt, float eps, int N, int HW, int C, int G,
+               float* ab, cudaStream_t st) {
+  if (check_shape(C, G)) return -1;
+  gn_ab_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, gamma, beta, pdt, eps, N, HW, C, G, ab);
+  VCD_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, float near_zero, int N, int HW, int C,
                             int G, vcd_stream_t stream) {

@@ -24,6 +24,7 @@ constexpr int kThreads = 384;    // warps 0-2: TMA / MMA / TMEM alloc, warp 3 id
 constexpr int kEpiWarps = 8;
 constexpr int kABytes = 23552;  // (8+2) x (16+2) rows x 128 B = 23040, rounded up to a multiple of 1024
 constexpr int kBStages = 8;
+constexpr int kChanAccBytes = 512 * 2 * 4;  // per-channel (sum g*x, sum g) of the fused GroupNorm backward, <= 512 channels
 
 template <int BLOCK_N>
 struct PCfg {
@@ -32,7 +33,8 @@ struct PCfg {
   static constexpr int kBBytes = kTapBytes * kTapsPerStage;
   static constexpr int kAStages = (BLOCK_N == 256) ? 3 : 4;
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes =
+      kAStages * kABytes + kBStages * kBBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kChanAccBytes;
 };
 
 struct TileCoord {
@@ -100,7 +102,24 @@ __device__ __forceinline__ float warp_reduce16(float* vals, int lane) {
   return vals[0] + __shfl_xor_sync(0xffffffffu, vals[0], 1);
 }
 
-template <int BLOCK_N>
+// sum 32 per-lane values over the 32 lanes of the warp in 31 shuffles: lane L ends with the warp total of vals[L]
+__device__ __forceinline__ float warp_reduce32(float* vals, int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int off = 16 >> step, half = 16 >> step;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = up ? vals[i + half] : vals[i];
+      const float send = up ? vals[i] : vals[i + half];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return vals[0];
+}
+
+// GNB: the epilogue is the fused GroupNorm backward prologue of a dgrad launch (no bias / residual / output sums)
+template <int BLOCK_N, bool GNB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ PairParams p) {
@@ -117,6 +136,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   auto tfull = [&](int s) { return bar_base + 8u * (2 * C::kAStages + 2 * kBStages + s); };
   auto tempty = [&](int s) { return bar_base + 8u * (2 * C::kAStages + 2 * kBStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::kAStages + 2 * kBStages + 4);
+  float* chan_acc = reinterpret_cast<float*>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));  // [Nout][2]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -141,6 +161,8 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (GNB)
+    for (int i = threadIdx.x; i < 2 * p.Nout; i += kThreads) chan_acc[i] = 0.f;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
                  "r"((uint32_t)C::kTmemCols)
@@ -253,31 +275,75 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int wi = row % tile_w, hi = row / tile_w;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cur_n = -1;  // image whose channel sums sit in chan_acc (fused GroupNorm backward)
+    // all 8 epilogue warps walk the same items: named barrier 1 (256 threads) brackets the flush of chan_acc
+    auto flush_chan_acc = [&]() {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = threadIdx.x - 128; i < 2 * p.Nout; i += 256) {
+        const float t = chan_acc[i];
+        if (t != 0.f) atomicAdd(p.gnb_dsdb + (long long)cur_n * 2 * p.Nout + i, t);
+        chan_acc[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     for (int item = cluster_id; item < p.total_items; item += n_clusters) {
       const int nt = item % p.n_tiles;
       const TileCoord tc = decode_tile(p, item / p.n_tiles, rank);
-      mbar_wait(tfull(acc), acc_phase);
-      tc_fence_after();
+      if (GNB && tc.valid && tc.n != cur_n) {
+        if (cur_n >= 0) flush_chan_acc();
+        cur_n = tc.n;
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       const int w = tc.w0 + wi, h = tc.h0 + hi;
       const bool valid = tc.valid && (w < p.W) && (h < p.H);
       const long long off =
           (long long)tc.n * p.out_sn + (long long)h * p.out_sh + (long long)w * p.out_sw + nt * BLOCK_N;
-#pragma unroll 1
-      for (int ch = chalf * (BLOCK_N / 64); ch < (chalf + 1) * (BLOCK_N / 64); ++ch) {
-        if (p.dbg & 1) break;
+      // side input of the epilogue (residual of a fprop, GroupNorm input of a fused dgrad): register double buffer,
+      // the first chunk is requested BEFORE waiting for the accumulator so its latency hides behind this item's MMAs
+      const bf16* side = GNB ? p.gnb_x : p.residual;
+      bf16x8 sb[2][4];
+      auto side_load = [&](int ch, bf16x8* dst) {
+        if (side != nullptr && valid && nt * BLOCK_N + ch * 32 + 32 <= p.Nout) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) dst[g] = ld8(side + off + ch * 32 + g * 8);
+        }
+      };
+      side_load(chalf * (BLOCK_N / 64), sb[0]);
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      // one 32-column chunk; `cur` holds the chunk's side input (residual or GroupNorm input), already loaded
+      auto process_chunk = [&](int ch, const bf16x8* cur) {
         uint32_t r[32];
         tmem_ld32(taddr + ch * 32, r);
         tmem_wait_ld();
         const int col0 = nt * BLOCK_N + ch * 32;
-        float gv[16];
+        float gv[GNB ? 1 : 16];
+        if (!GNB) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) gv[j] = 0.f;
+          for (int j = 0; j < 16; ++j) gv[j] = 0.f;
+        }
+        float v[32], xs[GNB ? 32 : 1];  // xs: GroupNorm input of the fused backward prologue, then g * x
+        if (GNB) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = xs[j] = 0.f;
+        }
         if (valid && col0 < p.Nout && !(p.dbg & 4)) {
-          float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          if (p.bias) {
+          if constexpr (GNB) {  // v = dL/d act(GN(x)) -> g = v * SiLU'(a x + b)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) unpack8(cur[g], xs + g * 8);
+            if (p.gnb_act) {
+              const float4* abp = reinterpret_cast<const float4*>(p.gnb_ab + ((long long)tc.n * p.Nout + col0) * 2);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 ab = __ldg(abp + j);
+                v[2 * j] *= silu_grad_f(fmaf(ab.x, xs[2 * j], ab.y));
+                v[2 * j + 1] *= silu_grad_f(fmaf(ab.z, xs[2 * j + 1], ab.w));
+              }
+            }
+          }
+          if (!GNB && p.bias) {
             const float* bp = p.bias + col0;
             if (col0 + 32 <= p.Nout) {
 #pragma unroll
@@ -291,13 +357,11 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 if (col0 + j < p.Nout) v[j] += __ldg(bp + j);
             }
           }
-          if (p.residual) {
-            const bf16* rp = p.residual + off + ch * 32;
+          if (!GNB && p.residual && col0 + 32 <= p.Nout) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float f[8];
-              if (col0 + g * 8 + 8 > p.Nout) continue;
-              unpack8(ld8(rp + g * 8), f);
+              unpack8(cur[g], f);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
             }
@@ -312,13 +376,25 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.Nout) op[j] = __float2bfloat16_rn(v[j]);
           }
-          if (p.gn_sums) {
-            if (p.gn_logD == 2) gn_partials<2>(v, gv);
-            else if (p.gn_logD == 3) gn_partials<3>(v, gv);
-            else gn_partials<4>(v, gv);
+          if constexpr (!GNB) {
+            if (p.gn_sums) {
+              if (p.gn_logD == 2) gn_partials<2>(v, gv);
+              else if (p.gn_logD == 3) gn_partials<3>(v, gv);
+              else gn_partials<4>(v, gv);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xs[j] *= v[j];
           }
         }
-        if (p.gn_sums && tc.valid && col0 < p.Nout) {  // warp-uniform: all 32 lanes take part in the shuffles
+        if constexpr (GNB) {
+          if (tc.valid && col0 < p.Nout) {  // warp-uniform
+          const float sgx = warp_reduce32(xs, lane);  // sum over the warp's 32 pixels of g * x, channel col0 + lane
+          const float sg = warp_reduce32(v, lane);    //                                  of g
+            atomicAdd(&chan_acc[(col0 + lane) * 2], sgx);
+            atomicAdd(&chan_acc[(col0 + lane) * 2 + 1], sg);
+          }
+        } else if (p.gn_sums && tc.valid && col0 < p.Nout) {  // warp-uniform: all 32 lanes take part in the shuffles
           const float tot = warp_reduce16(gv, lane);
           const int id = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
           if ((lane & 1) == 0 && id < (64 >> p.gn_logD)) {
@@ -327,12 +403,24 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             atomicAdd(p.gn_sums + ((long long)n_img * p.gn_G + group) * 2 + (id & 1), (double)tot);
           }
         }
+      };
+      if (!(p.dbg & 1)) {
+        constexpr int NCH = BLOCK_N / 64;  // chunks per warp
+        const int ch0 = chalf * NCH;
+#pragma unroll 1
+        for (int i = 0; i < NCH; i += 2) {
+          side_load(ch0 + i + 1, sb[1]);   // the next chunk's side input is in flight while this one is processed
+          process_chunk(ch0 + i, sb[0]);
+          if (i + 2 < NCH) side_load(ch0 + i + 2, sb[0]);
+          process_chunk(ch0 + i + 1, sb[1]);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty(acc) & kPeerBitMask);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (GNB && cur_n >= 0) flush_chan_acc();
   }
 
   tc_fence_before();
@@ -451,26 +539,27 @@ int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p,
   const int max_clusters = vcd_num_sms() / 2;
   const int clusters = p.total_items < max_clusters ? p.total_items : max_clusters;
   const int grid = clusters * 2;
-  if (block_n == 256) {
-    static bool attr = false;
-    if (!attr) {
-      VCD_CUDA(cudaFuncSetAttribute(umma_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    PCfg<256>::kSmemBytes));
-      attr = true;
+  const bool gnb = p.gnb_x != nullptr;
+  static bool attr_set[4] = {false, false, false, false};
+  auto launch = [&](auto kernel, int smem) -> int {
+    bool& done = attr_set[(block_n == 256 ? 2 : 0) + (gnb ? 1 : 0)];
+    if (!done) {
+      VCD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      done = true;
     }
-    umma_pair_kernel<256><<<grid, kThreads, PCfg<256>::kSmemBytes, st>>>(mapA, mapB, p);
-  } else if (block_n == 128) {
-    static bool attr = false;
-    if (!attr) {
-      VCD_CUDA(cudaFuncSetAttribute(umma_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    PCfg<128>::kSmemBytes));
-      attr = true;
-    }
-    umma_pair_kernel<128><<<grid, kThreads, PCfg<128>::kSmemBytes, st>>>(mapA, mapB, p);
-  } else {
+    kernel<<<grid, kThreads, smem, st>>>(mapA, mapB, p);
+    return 0;
+  };
+  int rc;
+  if (block_n == 256) rc = gnb ? launch(umma_pair_kernel<256, true>, PCfg<256>::kSmemBytes)
+                               : launch(umma_pair_kernel<256, false>, PCfg<256>::kSmemBytes);
+  else if (block_n == 128) rc = gnb ? launch(umma_pair_kernel<128, true>, PCfg<128>::kSmemBytes)
+                                    : launch(umma_pair_kernel<128, false>, PCfg<128>::kSmemBytes);
+  else {
     vcd_set_error("pair_launch: BLOCK_N %d unsupported", block_n);
     return -1;
   }
+  if (rc) return rc;
   VCD_LAUNCH_CHECK();
   return 0;
 }

@@ -50,6 +50,13 @@ struct PairParams {
   double* gn_sums;
   int gn_G, gn_logD;       // groups, log2(channels per group) in {2, 3, 4}
   int gn_rows_per_img;     // ROWS mode: rows of one image (a multiple of 128)
+  // fused GroupNorm backward prologue (dgrad of the conv that consumed act(GroupNorm(x))): the epilogue multiplies the
+  // data gradient by SiLU'(a x + b), stores that pre-activation gradient g, and accumulates sum_p g*x and sum_p g per
+  // (image, channel) into gnb_dsdb[n][c][2] (vcd_gn_bwd_reduce's result) — the GroupNorm backward then needs one pass
+  const bf16* gnb_x;       // GroupNorm input, same layout / strides as out
+  const float* gnb_ab;     // [N][C][2]: a = gamma * rstd, b = beta - mean * a
+  float* gnb_dsdb;         // [N][C][2] fp32, zeroed by the launcher
+  int gnb_act;             // 1: SiLU follows the GroupNorm
   int dbg;  // profiling aid (VCD_PAIR_DBG): 1 = epilogue only hand-shakes, 2 = MMA warp issues no MMAs, 4 = no stores
 };
 
@@ -59,6 +66,14 @@ struct GnEpilogue {
   int groups;
   bool fused;    // set by the launcher: the kernel produced the sums
   bool accumulate = false;  // add to sums already started by an earlier launch (phase convolutions): no zeroing
+};
+
+// fused GroupNorm backward prologue of a dgrad launch (host side)
+struct GnBwdPrologue {
+  const void* x;
+  const float* ab;
+  float* dsdb;
+  int act;
 };
 
 struct PairTap {

@@ -164,6 +164,15 @@ def pop_colsum(t: torch.Tensor):
 def clear_colsums() -> None:
     _COLSUMS.clear()
     _GNSUMS.clear()
+    _GN_FWD.clear()
+    _GN_BWD.clear()
+
+
+# GroupNorm -> conv backward fusion (vcd_conv2d_dgrad_gn).  _GN_FWD: output tensor of a GroupNorm(+SiLU) whose ONLY
+# consumer is a 3x3 conv -> what that conv's dgrad epilogue needs (x, sums, gamma, beta, eps, act, groups).
+# _GN_BWD: the tensor such a dgrad returned (g = dL/d(pre-activation)) -> the per-channel sums it already reduced.
+_GN_FWD = {}
+_GN_BWD = {}
 
 
 # GroupNorm sums (sum, sum of squares per (image, group)) of a tensor, produced by the epilogue of the GEMM that wrote
@@ -208,6 +217,12 @@ class _ConvFn(torch.autograd.Function):
              pad_t, pad_l, Ho, Wo, planes, impl, _p(sums), gn_groups, _st())
         if sums is not None:
             push_gn_sums(y, sums, gn_groups)
+        # x = act(GroupNorm(.)) with this conv as its only consumer: the dgrad epilogue will do the GroupNorm's reduction
+        gi = _GN_FWD.pop(x.data_ptr(), None)
+        ctx.gn_info = None
+        if (gi is not None and gi[0].shape == x.shape and umma and
+                _lib.lib().vcd_conv2d_dgrad_gn_supported(N, H, W, Cin, Cout, KH, KW, stride) == 1):
+            ctx.gn_info = gi[1:]
         ctx.save_for_backward(xs, weight, bias)
         ctx.packs = packs
         ctx.cfg = (N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl)
@@ -228,6 +243,15 @@ class _ConvFn(torch.autograd.Function):
                      pad_l, Ho, Wo, 1, impl, _st())
                 dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
                 call("vcd_planes_to_space", _p(dxp), _p(dx), N, H, W, Cin, _st())
+            elif ctx.gn_info is not None:
+                gx, gsums, ggamma, gbeta, geps, gact, ggroups = ctx.gn_info
+                dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
+                dsdb = torch.empty(N * Cin * 2, dtype=torch.float32, device=dy.device)
+                ab = torch.empty(N * Cin * 2, dtype=torch.float32, device=dy.device)
+                gg, gb = ggamma.detach(), gbeta.detach()
+                call("vcd_conv2d_dgrad_gn", _p(dy), _p(wd), _p(dx), N, H, W, Cin, Cout, KH, KW, pad_t, pad_l, _p(gx), _p(gsums),
+                     _p(gg), _p(gb), dtype_code(gg), ggroups, geps, gact, _p(dsdb), _p(ab), _st())
+                _GN_BWD[dx.data_ptr()] = (dx, dsdb)
             else:
                 dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
                 ws = _workspace("vcd_conv2d_dgrad_ws_bytes", (N, H, W, Cin, Cout, KH, KW, stride), impl, dy.device)
@@ -346,7 +370,7 @@ class _GroupNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, groups: int, eps: float, act: bool, slot_in: Optional[TrackSlot],
-                slot_out: Optional[TrackSlot], split: bool):
+                slot_out: Optional[TrackSlot], split: bool, sole_consumer_is_conv: bool = False):
         x = _nhwc(x)
         N, C = x.shape[0], x.shape[-1]
         hw = x.numel() // (N * C)
@@ -366,6 +390,8 @@ class _GroupNormFn(torch.autograd.Function):
             slot_out.finalize(N * hw)
         ctx.save_for_backward(x, sums, gamma, beta)
         ctx.cfg = (N, hw, C, groups, float(eps), 1 if act else 0)
+        if sole_consumer_is_conv and x.requires_grad:
+            _GN_FWD[out.data_ptr()] = (out, x, sums, gamma, beta, float(eps), 1 if act else 0, groups)
         if split:
             return out, x.view(x.shape)
         return out
@@ -379,8 +405,13 @@ class _GroupNormFn(torch.autograd.Function):
             dres = _nhwc(dres)
         g, b = gamma.detach(), beta.detach()
         pdt = dtype_code(g)
-        dsdb = torch.empty(N * C * 2, dtype=torch.float32, device=x.device)
-        call("vcd_gn_bwd_reduce", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), eps, act, N, hw, C, G, _st())
+        fused = _GN_BWD.pop(dout.data_ptr(), None)
+        if fused is not None and fused[0].shape == dout.shape:
+            # dout is already g = dL/d(pre-activation) and its channel sums were reduced by the conv's dgrad epilogue
+            dsdb, act = fused[1], 0
+        else:
+            dsdb = torch.empty(N * C * 2, dtype=torch.float32, device=x.device)
+            call("vcd_gn_bwd_reduce", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), eps, act, N, hw, C, G, _st())
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -391,11 +422,13 @@ class _GroupNormFn(torch.autograd.Function):
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(beta)
         call("vcd_gn_param_grad", _p(sums), _p(dsdb), _p(dgamma), _p(dbeta), pdt, eps, N, hw, C, G, _st())
-        return dx, dgamma, dbeta, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
-def group_norm(x, gamma, beta, groups, eps, act, slot_in=None, slot_out=None, split=False):
-    return _GroupNormFn.apply(x, gamma, beta, groups, eps, act, slot_in, slot_out, split)
+def group_norm(x, gamma, beta, groups, eps, act, slot_in=None, slot_out=None, split=False, sole_consumer_is_conv=False):
+    """sole_consumer_is_conv: the caller guarantees that the (first) output goes into exactly one ops.conv2d and nowhere
+    else — that conv's dgrad then performs SiLU' and the backward reduction of this GroupNorm in its epilogue."""
+    return _GroupNormFn.apply(x, gamma, beta, groups, eps, act, slot_in, slot_out, split, sole_consumer_is_conv)
 
 
 # ------------------------------------------------------------------------------------------

@@ -92,9 +92,9 @@ class B200GroupNorm(nn.GroupNorm):
         self._track_in: Optional[ops.TrackSlot] = None
         self._track_out: Optional[ops.TrackSlot] = None
 
-    def forward(self, x, act: bool = False, split: bool = False):
+    def forward(self, x, act: bool = False, split: bool = False, feeds_conv_only: bool = False):
         y = ops.group_norm(_phys(x), self.weight, self.bias, self.num_groups, self.eps, act,
-                           self._track_in, self._track_out, split)
+                           self._track_in, self._track_out, split, feeds_conv_only)
         if split:   # (normalised, input routed through for the block's skip connection)
             return _logi(y[0]), _logi(y[1])
         return _logi(y)
@@ -117,13 +117,15 @@ class B200Linear(nn.Linear):
         return y.reshape(N, T, -1)
 
 
-def _norm_act(norm: B200GroupNorm, x, split: bool = False):
+def _norm_act(norm: B200GroupNorm, x, split: bool = False, conv: Optional[nn.Module] = None):
     """GroupNorm followed by SiLU; unfused only when a foreign hook must observe the pre-activation.
-    split=True additionally returns the tensor the block's skip connection must use (see ops._GroupNormFn)."""
+    split=True additionally returns the tensor the block's skip connection must use (see ops._GroupNormFn).
+    conv: the conv that is the ONLY consumer of the result (its dgrad then carries this GroupNorm's backward
+    reduction, ops._GN_FWD); not used when either module carries a foreign hook."""
     if _hooked(norm):
         h = _logi(ops.silu(_phys(norm(x))))
         return (h, x) if split else h
-    return norm(x, act=True, split=split)
+    return norm(x, act=True, split=split, feeds_conv_only=conv is not None and not _hooked(conv))
 
 
 class ResnetBlock2D(nn.Module):
@@ -137,9 +139,9 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = B200Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h, x = _norm_act(self.norm1, x, split=True)
+        h, x = _norm_act(self.norm1, x, split=True, conv=self.conv1)
         h = self.conv1(h)
-        h = _norm_act(self.norm2, h)
+        h = _norm_act(self.norm2, h, conv=self.conv2)
         sc = x if self.conv_shortcut is None else self.conv_shortcut(x)
         if _hooked(self.conv2):
             return _logi(ops.add(_phys(self.conv2(h)), _phys(sc)))
