@@ -315,17 +315,50 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
   choose_tile(64, Wo, Ho, N, p);
   const int bn = pick_block_n(Cin);
   fill_fprop_taps(p, KH, KW, stride, pad_t, pad_l, 0);
-  p.n_tiles = Cin / bn;
+  if (pair_enabled() && Cout % 256 == 0) {  // CTA-pair kernel: M = 256 output channels per cluster
+    PairWgradParams q;
+    memset(&q, 0, sizeof(q));
+    q.W = p.W; q.H = p.H; q.Nimg = p.Nimg;
+    q.tile_w = p.tile_w; q.tile_h = p.tile_h; q.tile_n = p.tile_n;
+    q.tiles_w = p.tiles_w; q.tiles_h = p.tiles_h; q.tiles_n = p.tiles_n;
+    q.ntaps = p.ntaps;
+    for (int t = 0; t < p.ntaps; ++t) {
+      q.tap_dw[t] = p.tap_dw[t]; q.tap_dh[t] = p.tap_dh[t]; q.tap_plane[t] = p.tap_plane[t]; q.tap_plane_a[t] = 0;
+    }
+    q.m_pairs = Cout / 256;
+    q.n_tiles = Cin / bn;
+    q.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int base = q.ntaps * q.m_pairs * q.n_tiles, target = vcd_num_sms();  // two waves of 74 clusters
+    int splits = base >= target ? 1 : target / base;
+    if (splits > q.k_tiles) splits = q.k_tiles;
+    if (splits < 1) splits = 1;
+    q.k_per_split = (q.k_tiles + splits - 1) / splits;
+    q.splits = (q.k_tiles + q.k_per_split - 1) / q.k_per_split;
+    q.acc = ws; q.Mout = Cout; q.Nout = Cin;
+    CUtensorMap mA, mB;
+    int rc;
+    if ((rc = make_act_map(&mA, dy, Cout, Wo, Ho, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+    if (stride == 1) rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n);
+    else rc = make_act_map(&mB, x, Cin, W / 2, H / 2, 4, N, 64, p.tile_w, p.tile_h, p.tile_n);
+    if (rc) return rc;
+    return pair_wgrad_launch(mA, mB, q, bn, st);
+  }
+  // Cin = 128: one 256-column tile = two taps (umma_gemm.cuh tap_pairs)
+  const bool pairs = Cin == 128 && p.ntaps > 1;
+  const int bn_eff = pairs ? 256 : bn;
+  p.tap_pairs = pairs ? 1 : 0;
+  p.tap_items = pairs ? (p.ntaps + 1) / 2 : p.ntaps;
+  p.n_tiles = pairs ? 1 : Cin / bn;
   p.m_tiles = Cout / 128;
   p.Mout = Cout; p.Nout = Cin;
   p.acc = ws;
   p.batches = 1;
   p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int base_tiles = p.ntaps * p.m_tiles * p.n_tiles;
+  const int base_tiles = p.tap_items * p.m_tiles * p.n_tiles;
   int splits = pick_splits(base_tiles, p.k_tiles);
   p.k_per_split = (p.k_tiles + splits - 1) / splits;
   p.splits = (p.k_tiles + p.k_per_split - 1) / p.k_per_split;
-  set_form1_desc(p, bn);
+  set_form1_desc(p, bn_eff);
   p.total_tiles = base_tiles * p.splits;
   CUtensorMap mA, mB;
   int rc;
@@ -333,7 +366,7 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
   if (stride == 1) rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n);
   else rc = make_act_map(&mB, x, Cin, W / 2, H / 2, 4, N, 64, p.tile_w, p.tile_h, p.tile_n);
   if (rc) return rc;
-  return umma_launch(mA, mB, p, bn, st);
+  return umma_launch(mA, mB, p, bn_eff, st);
 }
 
 
@@ -432,6 +465,7 @@ int gemm_tn_impl(const void* A, const void* B, float* acc, int batch, int M, int
   p.acc = acc;
   p.batches = reduce_batch ? 1 : batch;
   p.k_tiles = reduce_batch ? p.tiles_w * batch : p.tiles_w;
+  p.tap_items = p.ntaps;
   const int base_tiles = p.batches * p.m_tiles * p.n_tiles;
   int splits = pick_splits(base_tiles, p.k_tiles);
   p.k_per_split = (p.k_tiles + splits - 1) / splits;
@@ -696,11 +730,38 @@ extern "C" int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw
     p.tap_dh[q] = dh - 1 + a; p.tap_dw[q] = dw_ - 1 + b; p.tap_plane[q] = 0;
     p.tap_plane_a[q] = a * 2 + b;
   }
+  if (pair_enabled() && Cout % 256 == 0) {  // CTA-pair kernel: M = 256 output channels per cluster
+    PairWgradParams q;
+    memset(&q, 0, sizeof(q));
+    q.W = p.W; q.H = p.H; q.Nimg = p.Nimg;
+    q.tile_w = p.tile_w; q.tile_h = p.tile_h; q.tile_n = p.tile_n;
+    q.tiles_w = p.tiles_w; q.tiles_h = p.tiles_h; q.tiles_n = p.tiles_n;
+    q.ntaps = 16;
+    for (int t = 0; t < 16; ++t) {
+      q.tap_dw[t] = p.tap_dw[t]; q.tap_dh[t] = p.tap_dh[t]; q.tap_plane[t] = 0; q.tap_plane_a[t] = p.tap_plane_a[t];
+    }
+    q.m_pairs = Cout / 256;
+    q.n_tiles = Cin / bn;
+    q.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int base = q.ntaps * q.m_pairs * q.n_tiles, target = vcd_num_sms();
+    int splits = base >= target ? 1 : target / base;
+    if (splits > q.k_tiles) splits = q.k_tiles;
+    if (splits < 1) splits = 1;
+    q.k_per_split = (q.k_tiles + splits - 1) / splits;
+    q.splits = (q.k_tiles + q.k_per_split - 1) / q.k_per_split;
+    q.acc = acc16; q.Mout = Cout; q.Nout = Cin;
+    CUtensorMap mA, mB;
+    int rc;
+    if ((rc = make_act_map(&mA, dy_planes, Cout, W, H, 4, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+    if ((rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+    if ((rc = pair_wgrad_launch(mA, mB, q, bn, st))) return rc;
+  } else {
   p.n_tiles = Cin / bn; p.m_tiles = Cout / 128;
   p.Mout = Cout; p.Nout = Cin;
   p.acc = acc16;
   p.batches = 1;
   p.k_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.tap_items = p.ntaps;
   const int base_tiles = p.ntaps * p.m_tiles * p.n_tiles;
   int splits = pick_splits(base_tiles, p.k_tiles);
   p.k_per_split = (p.k_tiles + splits - 1) / splits;
@@ -712,6 +773,8 @@ extern "C" int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw
   if ((rc = make_act_map(&mA, dy_planes, Cout, W, H, 4, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
   if ((rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
   if ((rc = umma_launch(mA, mB, p, bn, st))) return rc;
+  }
+  int rc;
   upconv_wgrad_combine_kernel<<<ew_blocks(main_elems), 256, 0, st>>>(acc16, wsf, Cout, Cin);
   VCD_LAUNCH_CHECK();
   if (db) {
@@ -814,10 +877,12 @@ extern "C" int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void*
 // ---- dgrad with the fused GroupNorm backward prologue (see include/vcd.h)
 extern "C" int vcd_conv2d_dgrad_gn_supported(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
   (void)N;
-  // Cin >= 256: with 128 channels the GEMM item (K = 1152) is too short to hide the ~900-instruction fused epilogue —
-  // measured on B200: +348 us on the dgrad against 210 us for the stand-alone vcd_gn_bwd_reduce (tools/prof_conv2.py)
+  // Cin, Cout >= 256 only: with 128 output channels per item column (N = 128) or a short reduction (K = 9 * Cout =
+  // 1152) the GEMM item is too short to hide the ~900-instruction fused epilogue — measured on B200: 128->128 @512^2
+  // +348 us on the dgrad against 210 us for the stand-alone vcd_gn_bwd_reduce; 256->128 +700 us against 410 us
+  // (tools/prof_conv2.py)
   return (pair_enabled() && umma_shape_ok(Cin, Cout, KH, KW, stride) && KH == 3 && KW == 3 && stride == 1 && W >= 8 &&
-          H >= 16 && Cin <= 512 && Cin >= 256 && Cin % 32 == 0) ? 1 : 0;
+          H >= 16 && Cin <= 512 && Cin >= 256 && Cout >= 256 && Cin % 32 == 0) ? 1 : 0;
 }
 extern "C" int vcd_conv2d_dgrad_gn(const void* dy, const void* w_dgrad, void* g_out, int N, int H, int W, int Cin, int Cout,
                                    int KH, int KW, int pad_t, int pad_l, const void* gn_x, const double* gn_sums,

@@ -39,8 +39,8 @@ __device__ __forceinline__ RedTile decode_red(const UmmaParams& p, int t) {
   // taps fastest: the CTAs running at the same time work on the SAME pixel range for all taps / channel tiles, so
   // the activation and gradient tiles are read from DRAM once and served from L2 to the other taps
   RedTile r;
-  r.tap = t % p.ntaps;
-  int q = t / p.ntaps;
+  r.tap = t % p.tap_items;
+  int q = t / p.tap_items;
   r.nt = q % p.n_tiles;
   q /= p.n_tiles;
   r.mt = q % p.m_tiles;
@@ -142,14 +142,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint32_t sa = smem_base + stage * C::kStageBytes;
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+            const int tap0 = p.tap_pairs ? rt.tap * 2 : rt.tap;
 #pragma unroll
             for (int b = 0; b < 2; ++b)
-              tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, pt.w0, pt.h0, p.tap_plane_a[rt.tap],
+              tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, pt.w0, pt.h0, p.tap_plane_a[tap0],
                           pt.n0);
 #pragma unroll
-            for (int b = 0; b < BLOCK_N / 64; ++b)
-              tma_load_5d(sa + kStageA + b * 8192, &mapB, full_bar(stage), rt.nt * BLOCK_N + b * 64,
-                          pt.w0 + p.tap_dw[rt.tap], pt.h0 + p.tap_dh[rt.tap], p.tap_plane[rt.tap], pt.n0);
+            for (int b = 0; b < BLOCK_N / 64; ++b) {
+              // tap_pairs: boxes 0,1 = tap 2g (channels 0-63, 64-127), boxes 2,3 = tap 2g+1 (the last odd tap is loaded
+              // twice; its duplicate columns are dropped by the epilogue)
+              const int tap = p.tap_pairs ? min(tap0 + (b >> 1), p.ntaps - 1) : tap0;
+              const int c0 = p.tap_pairs ? (b & 1) * 64 : rt.nt * BLOCK_N + b * 64;
+              tma_load_5d(sa + kStageA + b * 8192, &mapB, full_bar(stage), c0, pt.w0 + p.tap_dw[tap],
+                          pt.h0 + p.tap_dh[tap], p.tap_plane[tap], pt.n0);
+            }
           }
           __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -251,18 +257,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       } else {
         const RedTile rt = decode_red(p, tile);
-        float* op = p.acc +
-                    (((long long)rt.batch * p.ntaps + rt.tap) * p.Mout + rt.mt * 128 + row) * (long long)p.Nout +
-                    rt.nt * BLOCK_N;
 #pragma unroll 1
         for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
           uint32_t r[32];
           tmem_ld32(taddr + ch * 32, r);
           tmem_wait_ld();
-          if (rt.mt * 128 + row < p.Mout) {
+          // tap_pairs: columns [0,128) belong to tap 2g, [128,256) to tap 2g+1 (Nout = 128)
+          const int tap = p.tap_pairs ? rt.tap * 2 + (ch >> 2) : rt.tap;
+          const int col0 = p.tap_pairs ? (ch & 3) * 32 : rt.nt * BLOCK_N + ch * 32;
+          float* op = p.acc + (((long long)rt.batch * p.ntaps + tap) * p.Mout + rt.mt * 128 + row) * (long long)p.Nout + col0;
+          if (rt.mt * 128 + row < p.Mout && tap < p.ntaps) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (rt.nt * BLOCK_N + ch * 32 + j < p.Nout) atomicAdd(op + ch * 32 + j, __uint_as_float(r[j]));
+              if (col0 + j < p.Nout) atomicAdd(op + j, __uint_as_float(r[j]));
           }
         }
       }

@@ -45,6 +45,10 @@ struct UmmaParams {
   int m_tiles;  // Mout / 128
   int splits, k_per_split, k_tiles;  // pixel tiles per batch entry, split over CTAs
   int batches;  // 1 for conv wgrad (all images reduced), Nimg for attention (per-image result)
+  // form 1, Nout = 128 only: one BLOCK_N = 256 tile covers TWO taps x 128 input channels (columns 0-127: tap 2g,
+  // 128-255: tap 2g+1), so each MMA reads 4 KB of A for 256 columns instead of 128 (shared-memory operand bound)
+  int tap_pairs;
+  int tap_items;  // tiles along the tap axis: ntaps, or ceil(ntaps / 2) with tap_pairs
   // descriptor constants
   uint32_t a_desc_hi, b_desc_hi;   // upper 32 bits of the shared-memory matrix descriptors
   uint32_t a_lbo, b_lbo;           // leading byte offsets >> 4

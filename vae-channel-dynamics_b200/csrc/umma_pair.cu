@@ -433,6 +433,179 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
+// ====================================================================================================================
+// CTA-pair weight-gradient kernel (see umma_pair.cuh PairWgradParams)
+// ====================================================================================================================
+template <int BLOCK_N>
+struct WCfg {
+  static constexpr int kABytes = 16384;                 // 128 output channels x 64 pixels (2 boxes)
+  static constexpr int kBBytes = (BLOCK_N / 2) * 128;   // this CTA's half of the input channels x 64 pixels
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+};
+struct WItem {
+  int tap, nt, mp, k0, nk;
+};
+__device__ __forceinline__ WItem decode_witem(const PairWgradParams& p, int t) {
+  WItem r;  // taps fastest: clusters running together share the same pixel range in L2
+  r.tap = t % p.ntaps;
+  int q = t / p.ntaps;
+  r.nt = q % p.n_tiles;
+  q /= p.n_tiles;
+  r.mp = q % p.m_pairs;
+  const int split = q / p.m_pairs;
+  r.k0 = split * p.k_per_split;
+  r.nk = min(r.k0 + p.k_per_split, p.k_tiles) - r.k0;
+  return r;
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+umma_pair_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                       const __grid_constant__ PairWgradParams p) {
+  using C = WCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
+  auto tempty = [&](int s) { return bar_base + 8u * (2 * C::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull(s), 1);
+      mbar_init(tempty(s), 2 * kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ---------------- TMA producer (both CTAs)
+    if (elect_one_sync()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      const WItem it = decode_witem(p, item);
+      const int a_c0 = it.mp * 256 + rank * 128;
+      const int b_c0 = it.nt * BLOCK_N + rank * (BLOCK_N / 2);
+      for (int k = 0; k < it.nk; ++k) {
+        const int t = it.k0 + k;
+        const int tw = t % p.tiles_w, tq = t / p.tiles_w;
+        const int w0 = tw * p.tile_w, h0 = (tq % p.tiles_h) * p.tile_h, n0 = (tq / p.tiles_h) * p.tile_n;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint32_t lbar = full_bar(stage) & kPeerBitMask;
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * C::kStageBytes);
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            tma_load_5d_pair(sa + b * 8192, &mapA, lbar, a_c0 + b * 64, w0, h0, p.tap_plane_a[it.tap], n0);
+#pragma unroll
+          for (int b = 0; b < BLOCK_N / 128; ++b)
+            tma_load_5d_pair(sa + C::kABytes + b * 8192, &mapB, lbar, b_c0 + b * 64, w0 + p.tap_dw[it.tap],
+                             h0 + p.tap_dh[it.tap], p.tap_plane[it.tap], n0);
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ---------------- MMA issuer (leader)
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      const WItem it = decode_witem(p, item);
+      mbar_wait(tempty(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int k = 0; k < it.nk; ++k) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | ((8192u >> 4) << 16);               // LBO: next 64-channel box
+          const uint32_t b_lo = (((sa + C::kABytes) >> 4) & 0x3FFFu) | ((8192u >> 4) << 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)   // K = 16 pixels = 16 rows of 128 B per MMA
+            umma_bf16_pair(d_tmem, ((uint64_t)hi << 32) | (a_lo + j * (2048u >> 4)),
+                           ((uint64_t)hi << 32) | (b_lo + j * (2048u >> 4)), p.idesc, (k | j) != 0 ? 1u : 0u);
+          umma_commit_pair(empty_bar(stage));
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+      }
+      if (elect_one_sync()) umma_commit_pair(tfull(acc));
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (both CTAs): fp32 accumulators -> red.global.add
+    const int q = warp & 3, chalf = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      const WItem it = decode_witem(p, item);
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const int co = it.mp * 256 + rank * 128 + row;
+      float* op = p.acc + ((long long)it.tap * p.Mout + co) * (long long)p.Nout + it.nt * BLOCK_N;
+#pragma unroll 1
+      for (int ch = chalf * (BLOCK_N / 64); ch < (chalf + 1) * (BLOCK_N / 64); ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        tmem_wait_ld();
+        if (co < p.Mout) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (it.nt * BLOCK_N + ch * 32 + j < p.Nout) atomicAdd(op + ch * 32 + j, __uint_as_float(r[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty(acc) & kPeerBitMask);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+  }
+}
+
 uint32_t pair_idesc(int n) {
   // kind::f16: D = f32, A = B = bf16, both K-major, N >> 3, M = 256 >> 4
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24);
@@ -560,6 +733,38 @@ int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p,
     return -1;
   }
   if (rc) return rc;
+  VCD_LAUNCH_CHECK();
+  return 0;
+}
+
+int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgradParams& p, int block_n, cudaStream_t st) {
+  p.total_items = p.ntaps * p.n_tiles * p.m_pairs * p.splits;
+  if (p.total_items <= 0) return 0;
+  ++g_pair_launches;
+  // kind::f16: D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3, M = 256 >> 4
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(block_n >> 3) << 17) |
+            ((256u >> 4) << 24);
+  const int max_clusters = vcd_num_sms() / 2;
+  const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
+  static bool attr_set[2] = {false, false};
+  if (block_n == 256) {
+    if (!attr_set[0]) {
+      VCD_CUDA(cudaFuncSetAttribute(umma_pair_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    WCfg<256>::kSmemBytes));
+      attr_set[0] = true;
+    }
+    umma_pair_wgrad_kernel<256><<<grid, kThreads, WCfg<256>::kSmemBytes, st>>>(mapA, mapB, p);
+  } else if (block_n == 128) {
+    if (!attr_set[1]) {
+      VCD_CUDA(cudaFuncSetAttribute(umma_pair_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    WCfg<128>::kSmemBytes));
+      attr_set[1] = true;
+    }
+    umma_pair_wgrad_kernel<128><<<grid, kThreads, WCfg<128>::kSmemBytes, st>>>(mapA, mapB, p);
+  } else {
+    vcd_set_error("pair_wgrad_launch: BLOCK_N %d unsupported", block_n);
+    return -1;
+  }
   VCD_LAUNCH_CHECK();
   return 0;
 }

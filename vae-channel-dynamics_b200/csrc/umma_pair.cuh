@@ -80,6 +80,28 @@ struct PairTap {
   int plane, dh, dw, brow;
 };
 
+// ---- CTA-pair weight-gradient kernel: Dacc[tap][co][ci] += sum_pixels dy[pixel][co] * x[pixel + shift(tap)][ci]
+// M = 256 output channels (128 per CTA), N = BLOCK_N input channels (each CTA stages half of them), K = pixels in
+// steps of 64 (both operands MN-major 128B-swizzle boxes of 64 channels x 64 pixels), split over clusters (split-K),
+// fp32 red.global.add epilogue.  Per MMA each CTA reads 4 KB of A and 4 KB of B from shared memory (N = 256) instead of
+// 4 + 8 KB in the single-CTA kernel, which lifts the shared-memory operand bandwidth cap from 67 % to 100 % of the
+// tensor rate.
+struct PairWgradParams {
+  int W, H, Nimg;
+  int tile_w, tile_h, tile_n;     // the 64-pixel K-step box
+  int tiles_w, tiles_h, tiles_n;
+  int ntaps;
+  int tap_dw[16], tap_dh[16], tap_plane[16], tap_plane_a[16];
+  int m_pairs;                    // Cout / 256
+  int n_tiles;                    // Cin / BLOCK_N
+  int splits, k_per_split, k_tiles;
+  float* acc;                     // [tap][Mout][Nout] fp32
+  int Mout, Nout;
+  uint32_t idesc;
+  int total_items;
+};
+int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgradParams& p, int block_n, cudaStream_t st);
+
 // fills mode / tiling / groups / taps / descriptors of a HALO launch; returns false when the shape is not eligible
 bool pair_setup_halo(PairParams& p, int W, int H, int N, const PairTap* taps, int ntaps, int block_n, int* box_h_out);
 void pair_setup_rows(PairParams& p, int rows, int batch, int pair_in_image, int brow, int block_n);
