@@ -26,6 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "SDXL-VAE train images/sec at 512^2 (tracking on)"
+
+
+def metric_name(res):
+    return METRIC if res == 512 else f"SDXL-VAE train images/sec at {res}^2 (tracking on)"
 UNIT = "images/s"
 
 
@@ -50,34 +54,35 @@ def parse():
 
 # ------------------------------------------------------------------------------------------ FLOP model
 def conv_layers(R):
-    """(Cin, Cout, k, out_h) of every conv of the SDXL VAE for an RxR input."""
+    """(Cin, Cout, k, out_h, kind) of every conv of the SDXL VAE for an RxR input.
+    kind: "s1" stride-1 conv, "down" Downsample2D (pad (0,1,0,1), stride 2), "up" Upsample2D (nearest x2 + conv)."""
     L = []
     def res(ci, co, h):
-        L.extend([(ci, co, 3, h), (co, co, 3, h)])
+        L.extend([(ci, co, 3, h, "s1"), (co, co, 3, h, "s1")])
         if ci != co:
-            L.append((ci, co, 1, h))
-    L.append((3, 128, 3, R))
-    res(128, 128, R); res(128, 128, R); L.append((128, 128, 3, R // 2))
-    res(128, 256, R // 2); res(256, 256, R // 2); L.append((256, 256, 3, R // 4))
-    res(256, 512, R // 4); res(512, 512, R // 4); L.append((512, 512, 3, R // 8))
+            L.append((ci, co, 1, h, "s1"))
+    L.append((3, 128, 3, R, "s1"))
+    res(128, 128, R); res(128, 128, R); L.append((128, 128, 3, R // 2, "down"))
+    res(128, 256, R // 2); res(256, 256, R // 2); L.append((256, 256, 3, R // 4, "down"))
+    res(256, 512, R // 4); res(512, 512, R // 4); L.append((512, 512, 3, R // 8, "down"))
     for _ in range(4):
         res(512, 512, R // 8)                      # down3 x2, mid x2
-    L.append((512, 8, 3, R // 8)); L.append((8, 8, 1, R // 8)); L.append((4, 4, 1, R // 8))
-    L.append((4, 512, 3, R // 8))
+    L.append((512, 8, 3, R // 8, "s1")); L.append((8, 8, 1, R // 8, "s1")); L.append((4, 4, 1, R // 8, "s1"))
+    L.append((4, 512, 3, R // 8, "s1"))
     for _ in range(5):
         res(512, 512, R // 8)                      # mid x2, up0 x3
-    L.append((512, 512, 3, R // 4))
+    L.append((512, 512, 3, R // 4, "up"))
     for _ in range(3):
         res(512, 512, R // 4)
-    L.append((512, 512, 3, R // 2))
-    res(512, 256, R // 2); res(256, 256, R // 2); res(256, 256, R // 2); L.append((256, 256, 3, R))
+    L.append((512, 512, 3, R // 2, "up"))
+    res(512, 256, R // 2); res(256, 256, R // 2); res(256, 256, R // 2); L.append((256, 256, 3, R, "up"))
     res(256, 128, R); res(128, 128, R); res(128, 128, R)
-    L.append((128, 3, 3, R))
+    L.append((128, 3, 3, R, "s1"))
     return L
 
 
 def train_flops_per_image(R):
-    conv = sum(2.0 * h * h * co * ci * k * k for ci, co, k, h in conv_layers(R))
+    conv = sum(2.0 * h * h * co * ci * k * k for ci, co, k, h, _ in conv_layers(R))
     T = (R // 8) ** 2
     attn = 2 * (4 * 2.0 * T * 512 * 512 + 2 * 2.0 * T * T * 512)
     return 3.0 * (conv + attn), conv, attn
@@ -203,7 +208,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = (f"{args.steps} timed + {args.warmup} warm-up full training steps (fwd+loss+bwd+clip+AdamW+tracker) of the "
               f"oracle at B=1, {r}x{r}, fp32, {cores} host threads; images/s scaled by ({r}/{args.res})^2 to {args.res}^2")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": metric_name(args.res), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"experiment_fonts_nudge: synthetic {args.res}^2 glyph-like images, tracking + nudge, "
@@ -216,26 +221,33 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ kernel roofline pass
 def conv_roofline(torch, vcd, R, B, peaks):
-    """CUDA-event timing of the tcgen05 implicit-GEMM kernel on every distinct GEMM-path conv shape of the
-    model (fprop, dgrad, wgrad), inputs rotated through > 126 MB so nothing is L2-resident.  achieved =
-    algorithmic FLOPs (2*M*N*K per pass) / measured time, summed with the per-step multiplicity."""
+    """CUDA-event timing of the tcgen05 implicit-GEMM kernels on every distinct GEMM-path conv of the model (fprop +
+    dgrad + wgrad through the C ABI, as the training step issues them), inputs rotated through > 126 MB so nothing is
+    L2-resident.  achieved = EXECUTED FLOPs / measured time summed with the per-step multiplicity: 2*M*N*K per pass
+    for ordinary convs; the three Upsample2D convs run as four 2x2 phase convolutions on the
+    low-resolution tensor, i.e. 16/36 of the reference formulation's multiply-adds, and only those are counted."""
     ops = vcd.ops
     from collections import Counter
-    shapes = Counter((ci, co, k, h) for ci, co, k, h in conv_layers(R) if ci % 128 == 0 and co % 128 == 0)
-    tot_f = tot_t = 0.0
+    shapes = Counter(l for l in conv_layers(R) if l[0] % 128 == 0 and l[1] % 128 == 0)
+    tot_f = tot_t = ref_f = 0.0
     per_shape = []
-    for (ci, co, k, h), cnt in sorted(shapes.items()):
-        nbuf = max(2, int(200e6 // (B * h * h * ci * 2)) + 1)
-        nbuf = min(nbuf, 8)
-        xs = [torch.randn(B, h, h, ci, device="cuda").to(torch.bfloat16).requires_grad_() for _ in range(nbuf)]
+    for (ci, co, k, h, kind), cnt in sorted(shapes.items()):
+        hin = h // 2 if kind == "up" else (2 * h if kind == "down" else h)
+        nbuf = min(8, max(2, int(200e6 // (B * hin * hin * ci * 2)) + 1))
+        xs = [torch.randn(B, hin, hin, ci, device="cuda").to(torch.bfloat16).requires_grad_() for _ in range(nbuf)]
         w = (torch.randn(co, ci, k, k, device="cuda") * 0.02).to(torch.bfloat16).requires_grad_()
         bias = torch.zeros(co, device="cuda", dtype=torch.bfloat16).requires_grad_()
-        packs = ops.PackedWeights()
         pad = 1 if k == 3 else 0
         g = torch.randn(B, h, h, co, device="cuda").to(torch.bfloat16)
-        def run(i):
-            y = ops.conv2d(xs[i % nbuf], w, bias, packs, stride=1, pad_t=pad, pad_l=pad)
-            y.backward(g)
+        if kind == "up":
+            packs = ops.UpconvPackedWeights()
+            run = lambda i: ops.upconv2d(xs[i % nbuf], w, bias, packs).backward(g)
+        elif kind == "down":
+            packs = ops.PackedWeights()
+            run = lambda i: ops.conv2d(xs[i % nbuf], w, bias, packs, stride=2, pad_t=0, pad_l=0, out_hw=(h, h)).backward(g)
+        else:
+            packs = ops.PackedWeights()
+            run = lambda i: ops.conv2d(xs[i % nbuf], w, bias, packs, stride=1, pad_t=pad, pad_l=pad).backward(g)
         for i in range(3):
             run(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,42 +259,76 @@ def conv_roofline(torch, vcd, R, B, peaks):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        fl = 3 * 2.0 * B * h * h * co * ci * k * k
-        per_shape.append({"shape": f"{ci}->{co} k{k} @{h}", "count": cnt, "ms_fwd_bwd": ms, "tflops": fl / ms / 1e9})
+        ref = 3 * 2.0 * B * h * h * co * ci * k * k
+        fl = ref * 16.0 / 36.0 if kind == "up" else ref
+        per_shape.append({"shape": f"{ci}->{co} k{k} {kind} out@{h}", "count": cnt, "ms_fwd_bwd": ms, "tflops": fl / ms / 1e9})
         tot_f += fl * cnt
+        ref_f += ref * cnt
         tot_t += ms * cnt
         del xs, w, g
     achieved = tot_f / tot_t / 1e9
     peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_conv_summary.json")) as f:
+            traffic = json.load(f).get("dominant_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "umma_gemm_kernel (fprop+dgrad+wgrad incl. bias-grad/finalize)",
+            "traffic": traffic,
+            "kernel": "umma_pair_kernel / umma_pair_wgrad_kernel / umma_gemm_kernel (fprop+dgrad+wgrad incl. weight packs, "
+                      "bias-grad and finalize kernels; executed FLOPs)",
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback",
+            "reference_formulation_tflops": ref_f / tot_t / 1e9,
             "per_shape": per_shape, "conv_ms_per_step": tot_t}
 
 
 def gn_roofline(torch, vcd, R, B, peaks):
-    ops = vcd.ops
-    C, h = 128, R
-    n = 3
+    """HBM roofline of the GroupNorm kernels on the largest tensor class of the model (128 channels at full
+    resolution): algorithmic bytes (forward 4 B/element, backward reduce 4, backward apply 6 or 8 with the
+    skip gradient) / CUDA-event time per kernel.  The forward statistics come from the producing conv's epilogue."""
+    from vcd_b200.ops import _p, _st, call, dtype_code
+    C, h, n = 128, R, 3
     xs = [torch.randn(B, h, h, C, device="cuda").to(torch.bfloat16) for _ in range(n)]
+    gs = [torch.randn(B, h, h, C, device="cuda").to(torch.bfloat16) for _ in range(n)]
+    out = torch.empty_like(xs[0])
     gamma = torch.ones(C, device="cuda", dtype=torch.bfloat16)
     beta = torch.zeros(C, device="cuda", dtype=torch.bfloat16)
-    slot = ops.TrackSlot(C, "cuda", 0.0)
-    for i in range(2):
-        ops.group_norm(xs[i], gamma, beta, 32, 1e-6, True, None, slot)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(6):
-        ops.group_norm(xs[i % n], gamma, beta, 32, 1e-6, True, None, slot)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 6
-    bytes_alg = 4.0 * B * h * h * C     # read x + write y (bf16); statistics add none
+    sums = torch.empty(B * 32 * 2, dtype=torch.float64, device="cuda")
+    dsdb = torch.empty(B * C * 2, dtype=torch.float32, device="cuda")
+    colsum = torch.empty(C, dtype=torch.float32, device="cuda")
+    slot = vcd.ops.TrackSlot(C, "cuda", 0.0)
+    pdt, hw, ne = dtype_code(gamma), h * h, B * h * h * C
+    call("vcd_gn_stats", _p(xs[0]), _p(sums), None, 0.0, B, hw, C, 32, _st())
+    kernels = {
+        "gn_apply_fwd(+SiLU, +per-channel statistics)": (4, lambda i: call(
+            "vcd_gn_apply_fwd", _p(xs[i % n]), _p(sums), _p(gamma), _p(beta), pdt, _p(out), _p(slot.raw), 0.0, 1e-6, 1, B, hw, C,
+            32, _st())),
+        "gn_bwd_reduce": (4, lambda i: call(
+            "vcd_gn_bwd_reduce", _p(xs[i % n]), _p(gs[i % n]), _p(sums), _p(gamma), _p(beta), pdt, _p(dsdb), 1e-6, 1, B, hw, C, 32,
+            _st())),
+        "gn_bwd_apply(+skip gradient, +bias-gradient column sums)": (8, lambda i: call(
+            "vcd_gn_bwd_apply", _p(xs[i % n]), _p(gs[i % n]), _p(sums), _p(gamma), _p(beta), pdt, _p(dsdb), _p(out),
+            _p(gs[(i + 1) % n]), _p(colsum), 1e-6, 1, B, hw, C, 32, _st())),
+    }
     peak = peaks.get("hbm_gbs", 6650.0)
-    ach = bytes_alg / ms / 1e6
-    return {"bound": "hbm", "kernel": "gn_stats + gn_apply(+SiLU +channel stats) forward, 128ch full-res", "achieved": ach,
-            "peak": peak, "unit": "GB/s", "frac": ach / peak, "ms": ms}
+    res = []
+    for name, (bpe, fn) in kernels.items():
+        for i in range(2):
+            fn(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(6):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 6
+        ach = bpe * ne / ms / 1e6
+        res.append({"kernel": name, "bytes_per_element": bpe, "ms": ms, "achieved": ach, "frac": ach / peak})
+    worst = min(res, key=lambda r: r["frac"])
+    return {"bound": "hbm", "unit": "GB/s", "peak": peak, "tensor": f"[{B},{h},{h},{C}] bf16", "kernels": res,
+            "achieved": worst["achieved"], "frac": worst["frac"], "kernel": worst["kernel"]}
 
 
 # ------------------------------------------------------------------------------------------ main (B200 arm)
@@ -435,7 +481,7 @@ def main():
         fl_img, _, _ = train_flops_per_image(R)
         peak_t = peaks.get("bf16_tflops_sustained", 1414.5)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "metric": metric_name(R), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"experiment_fonts_nudge: synthetic {R}^2 glyph-like images, tracking (3 layers) every forward, "
