@@ -57,8 +57,9 @@ int vcd_pack_conv_weight(const void* w, const void* bias, int dtype, int Cout, i
  * y[n,ho,wo,co] = bias[co] + sum x[n, ho*stride - pad_t + kh, wo*stride - pad_l + kw, ci] * w[co,ci,kh,kw]
  *                 (+ residual[n,ho,wo,co])
  * Downsample2D's asymmetric (0,1,0,1) pad is pad_t = pad_l = 0 with Ho = H/2 (zero fill
- * past the bottom/right edge).  x_planes != 0 (stride 2 only) means x is the parity-plane
- * layout [N][2][2][H/2][W/2][C] written by vcd_space_to_planes. */
+ * past the bottom/right edge).  Stride-2 layers read the NHWC tensor in place (x_planes = 0: the tcgen05 path uses
+ * element-strided TMA maps); x_planes != 0 means x is the parity-plane layout [N][2][2][H/2][W/2][C] written by
+ * vcd_space_to_planes (kept for callers that already hold that layout). */
 int64_t vcd_conv2d_fprop_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
 /* gn_sums (fp64 [N][gn_groups][2], may be NULL): on return holds sum and sum of squares of y per (image, group) —
  * the statistics the GroupNorm that consumes y needs (vcd_gn_apply_fwd), produced by the GEMM epilogue when the
@@ -95,7 +96,8 @@ int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, const fl
  * tensor with pre-summed weights ([upstream] Upsample2D in decoder.up_blocks.{0,1,2}.upsamplers.0).
  * 16 tap products per low-res pixel instead of 36; the upsampled tensor is never materialised.
  *   wf16: bf16 [16][Cout][Cin], wd16: bf16 [16][Cin][Cout]  (index ((a*2+b)*2+dh)*2+dw)
- *   x [N][H][W][Cin] -> y [N][2H][2W][Cout];  dy_planes = vcd_space_to_planes(dy) = [N][2][2][H][W][Cout] */
+ *   x [N][H][W][Cin] -> y [N][2H][2W][Cout];  the backward entry points take dy [N][2H][2W][Cout] as stored: its four
+ *   parity planes are read in place through element-strided TMA maps (no space-to-planes copy) */
 int vcd_pack_upconv_weight(const void* w, const void* bias, int dtype, int Cout, int Cin, void* wf16, void* wd16,
                            float* bias_f32, vcd_stream_t stream);
 int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* bias, void* y, int N, int H, int W, int Cin,

@@ -102,7 +102,7 @@ int attach_gn(PairParams& p, GnEpilogue* gn, int n_images, int Nout, int rows_pe
 int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, int Ht, const PairTap* taps, int ntaps,
                   const void* wpack, int wrows, const float* bias, const void* residual, void* out, long long sn,
                   long long sh, long long sw, int Nout, cudaStream_t st, GnEpilogue* gn = nullptr,
-                  const GnBwdPrologue* gnb = nullptr) {
+                  const GnBwdPrologue* gnb = nullptr, int es = 1) {
   if (!pair_enabled() || C % 64 != 0) return 0;
   PairParams p;
   memset(&p, 0, sizeof(p));
@@ -123,7 +123,8 @@ int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, 
     p.gnb_x = (const bf16*)gnb->x; p.gnb_ab = gnb->ab; p.gnb_dsdb = gnb->dsdb; p.gnb_act = gnb->act;
     VCD_CUDA(cudaMemsetAsync(gnb->dsdb, 0, sizeof(float) * 2 * N * Nout, st));
   }
-  if ((rc = make_act_map(&mA, act, C, Wa, Ha, P, N, 64, p.box_w, box_h, 1))) return rc;
+  p.a_es = es;
+  if ((rc = make_act_map(&mA, act, C, Wa, Ha, P, N, 64, p.box_w, box_h, 1, es))) return rc;
   if ((rc = make_act_map(&mB, wpack, C, wrows, 1, 1, 1, 64, bn / 2, 1, 1))) return rc;
   if ((rc = pair_launch(mA, mB, p, bn, st))) return rc;
   return 1;
@@ -182,8 +183,10 @@ int umma_fprop(const void* x, const void* wf, const float* bias, const void* res
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.form = 0;
-  VCD_CHECK_ARG(stride == 1 || x_planes, "tcgen05 stride-2 conv needs the parity-plane input (vcd_space_to_planes)");
   VCD_CHECK_ARG(stride == 2 || (Ho == H && Wo == W), "tcgen05 conv: stride-1 convs must preserve the spatial size");
+  // stride 2: parity planes are either a physical layout (x_planes, vcd_space_to_planes) or, by default, read in place
+  // from the NHWC tensor through an element-strided TMA map (make_act_map es = 2)
+  const int es = (stride == 2 && !x_planes) ? 2 : 1;
   choose_tile(128, Wo, Ho, N, p);
   const int bn = pick_block_n(Cout);
   fill_fprop_taps(p, KH, KW, stride, pad_t, pad_l, Cout);
@@ -197,8 +200,11 @@ int umma_fprop(const void* x, const void* wf, const float* bias, const void* res
     for (int t = 0; t < p.ntaps; ++t) taps[t] = PairTap{p.tap_plane[t], p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
     rc = stride == 1 ? try_pair_halo(x, Cin, W, H, 1, N, Wo, Ho, taps, p.ntaps, wf, KH * KW * Cout, bias, residual, y,
                                      (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st, gn)
-                     : try_pair_halo(x, Cin, W / 2, H / 2, 4, N, Wo, Ho, taps, p.ntaps, wf, KH * KW * Cout, bias, residual,
-                                     y, (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st, gn);
+                     : es == 2
+                           ? try_pair_halo(x, Cin, W, H, 1, N, Wo, Ho, taps, p.ntaps, wf, KH * KW * Cout, bias, residual, y,
+                                           (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st, gn, nullptr, 2)
+                           : try_pair_halo(x, Cin, W / 2, H / 2, 4, N, Wo, Ho, taps, p.ntaps, wf, KH * KW * Cout, bias,
+                                           residual, y, (long long)Ho * Wo * Cout, (long long)Wo * Cout, Cout, Cout, st, gn);
     if (rc != 0) return rc < 0 ? rc : 0;
   }
   p.n_tiles = Cout / bn;
@@ -211,7 +217,8 @@ int umma_fprop(const void* x, const void* wf, const float* bias, const void* res
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   CUtensorMap mA, mB;
   int rc;
-  if (stride == 1) rc = make_act_map(&mA, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n);
+  p.a_es = es;
+  if (stride == 1 || es == 2) rc = make_act_map(&mA, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n, es);
   else rc = make_act_map(&mA, x, Cin, W / 2, H / 2, 4, N, 64, p.tile_w, p.tile_h, p.tile_n);
   if (rc) return rc;
   if ((rc = make_act_map(&mB, wf, Cin, KH * KW * Cout, 1, 1, 1, 64, bn, 1, 1))) return rc;
@@ -258,8 +265,8 @@ int umma_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, in
     if ((rc = make_act_map(&mB, wd, Cout, KH * KW * Cin, 1, 1, 1, 64, bn, 1, 1))) return rc;
     return umma_launch(mA, mB, p, bn, st);
   }
-  // stride 2: one launch per parity plane of dx (plane (ph,pw) receives the taps with matching parity)
-  VCD_CHECK_ARG(dx_planes, "tcgen05 stride-2 dgrad writes the parity-plane layout (dx_planes = 1)");
+  // stride 2: one launch per parity plane of dx (plane (ph,pw) receives the taps with matching parity); the plane is
+  // either a slab of the parity-plane layout (dx_planes) or a strided view of the NHWC tensor written in place
   const int H2 = H / 2, W2 = W / 2;
   for (int ph = 0; ph < 2; ++ph)
     for (int pw = 0; pw < 2; ++pw) {
@@ -277,8 +284,12 @@ int umma_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, in
           ++nt;
         }
       const long long plane_elems = (long long)H2 * W2 * Cin;
-      bf16* outp = (bf16*)dx + (ph * 2 + pw) * plane_elems;
+      bf16* outp = dx_planes ? (bf16*)dx + (ph * 2 + pw) * plane_elems : (bf16*)dx + ((long long)ph * W + pw) * Cin;
+      const long long o_sn = 4 * plane_elems;
+      const long long o_sh = dx_planes ? (long long)W2 * Cin : 2ll * W * Cin;
+      const long long o_sw = dx_planes ? Cin : 2ll * Cin;
       if (nt == 0) {  // no tap reaches this plane: its gradient is zero
+        VCD_CHECK_ARG(dx_planes, "stride-2 dgrad: a parity plane without taps needs the plane layout");
         for (int n = 0; n < N; ++n)
           VCD_CUDA(cudaMemsetAsync(outp + n * 4 * plane_elems, 0, plane_elems * sizeof(bf16), st));
         continue;
@@ -287,14 +298,14 @@ int umma_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, in
       {
         PairTap taps[16];
         for (int t = 0; t < nt; ++t) taps[t] = PairTap{0, p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
-        rc = try_pair_halo(dy, Cout, Wo, Ho, 1, N, W2, H2, taps, nt, wd, KH * KW * Cin, nullptr, nullptr, outp,
-                           4 * plane_elems, (long long)W2 * Cin, Cin, Cin, st);
+        rc = try_pair_halo(dy, Cout, Wo, Ho, 1, N, W2, H2, taps, nt, wd, KH * KW * Cin, nullptr, nullptr, outp, o_sn, o_sh,
+                           o_sw, Cin, st);
         if (rc < 0) return rc;
         if (rc == 1) continue;
       }
       p.n_tiles = Cin / bn; p.kc_per_tap = Cout / 64;
       p.out = outp; p.alpha = 1.f;
-      p.out_sn = 4 * plane_elems; p.out_sh = (long long)W2 * Cin; p.out_sw = Cin;
+      p.out_sn = o_sn; p.out_sh = o_sh; p.out_sw = o_sw;
       p.Nout = Cin;
       set_form0_desc(p, bn);
       p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
@@ -311,7 +322,7 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.form = 1;
-  VCD_CHECK_ARG(stride == 1 || x_planes, "tcgen05 stride-2 wgrad needs the parity-plane input");
+  const int es = (stride == 2 && !x_planes) ? 2 : 1;  // stride 2 without the plane layout: element-strided TMA map
   choose_tile(64, Wo, Ho, N, p);
   const int bn = pick_block_n(Cin);
   fill_fprop_taps(p, KH, KW, stride, pad_t, pad_l, 0);
@@ -337,8 +348,9 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
     q.acc = ws; q.Mout = Cout; q.Nout = Cin;
     CUtensorMap mA, mB;
     int rc;
+    q.b_es = es;
     if ((rc = make_act_map(&mA, dy, Cout, Wo, Ho, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
-    if (stride == 1) rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n);
+    if (stride == 1 || es == 2) rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n, es);
     else rc = make_act_map(&mB, x, Cin, W / 2, H / 2, 4, N, 64, p.tile_w, p.tile_h, p.tile_n);
     if (rc) return rc;
     return pair_wgrad_launch(mA, mB, q, bn, st);
@@ -362,8 +374,9 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
   p.total_tiles = base_tiles * p.splits;
   CUtensorMap mA, mB;
   int rc;
+  p.b_es = es;
   if ((rc = make_act_map(&mA, dy, Cout, Wo, Ho, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
-  if (stride == 1) rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n);
+  if (stride == 1 || es == 2) rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n, es);
   else rc = make_act_map(&mB, x, Cin, W / 2, H / 2, 4, N, 64, p.tile_w, p.tile_h, p.tile_n);
   if (rc) return rc;
   return umma_launch(mA, mB, p, bn_eff, st);
@@ -669,7 +682,7 @@ extern "C" int vcd_upconv2d_fprop(const void* x, const void* wf16, const float* 
   return 0;
 }
 
-// dy_planes [N][2][2][H][W][Cout] (vcd_space_to_planes of dy [N][2H][2W][Cout]) -> dx [N][H][W][Cin]
+// dy [N][2H][2W][Cout] (its four parity planes are read in place through an element-strided TMA map) -> dx [N][H][W][Cin]
 extern "C" int vcd_upconv2d_dgrad(const void* dy_planes, const void* wd16, void* dx, int N, int H, int W, int Cin,
                                   int Cout, vcd_stream_t stream) {
   VCD_CHECK_ARG(dy_planes && wd16 && dx, "upconv dgrad: null pointer");
@@ -688,8 +701,8 @@ extern "C" int vcd_upconv2d_dgrad(const void* dy_planes, const void* wd16, void*
   {
     PairTap taps[16];
     for (int t = 0; t < 16; ++t) taps[t] = PairTap{p.tap_plane[t], p.tap_dh[t], p.tap_dw[t], p.tap_brow[t]};
-    int prc = try_pair_halo(dy_planes, Cout, W, H, 4, N, W, H, taps, 16, wd16, 16 * Cin, nullptr, nullptr, dx,
-                            (long long)H * W * Cin, (long long)W * Cin, Cin, Cin, as_stream(stream));
+    int prc = try_pair_halo(dy_planes, Cout, 2 * W, 2 * H, 1, N, W, H, taps, 16, wd16, 16 * Cin, nullptr, nullptr, dx,
+                            (long long)H * W * Cin, (long long)W * Cin, Cin, Cin, as_stream(stream), nullptr, nullptr, 2);
     if (prc != 0) return prc < 0 ? prc : 0;
   }
   p.n_tiles = Cin / bn; p.kc_per_tap = Cout / 64;
@@ -700,7 +713,8 @@ extern "C" int vcd_upconv2d_dgrad(const void* dy_planes, const void* wd16, void*
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   CUtensorMap mA, mB;
   int rc;
-  if ((rc = make_act_map(&mA, dy_planes, Cout, W, H, 4, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+  p.a_es = 2;
+  if ((rc = make_act_map(&mA, dy_planes, Cout, 2 * W, 2 * H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n, 2))) return rc;
   if ((rc = make_act_map(&mB, wd16, Cout, 16 * Cin, 1, 1, 1, 64, bn, 1, 1))) return rc;
   return umma_launch(mA, mB, p, bn, as_stream(stream));
 }
@@ -752,7 +766,8 @@ extern "C" int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw
     q.acc = acc16; q.Mout = Cout; q.Nout = Cin;
     CUtensorMap mA, mB;
     int rc;
-    if ((rc = make_act_map(&mA, dy_planes, Cout, W, H, 4, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+    q.a_es = 2;
+    if ((rc = make_act_map(&mA, dy_planes, Cout, 2 * W, 2 * H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n, 2))) return rc;
     if ((rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
     if ((rc = pair_wgrad_launch(mA, mB, q, bn, st))) return rc;
   } else {
@@ -770,7 +785,8 @@ extern "C" int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw
   p.total_tiles = base_tiles * p.splits;
   CUtensorMap mA, mB;
   int rc;
-  if ((rc = make_act_map(&mA, dy_planes, Cout, W, H, 4, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
+  p.a_es = 2;
+  if ((rc = make_act_map(&mA, dy_planes, Cout, 2 * W, 2 * H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n, 2))) return rc;
   if ((rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n))) return rc;
   if ((rc = umma_launch(mA, mB, p, bn, st))) return rc;
   }

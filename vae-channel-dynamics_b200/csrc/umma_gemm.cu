@@ -123,8 +123,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint32_t sa = smem_base + stage * C::kStageBytes;
             if (elect_one_sync()) {
               mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
-              tma_load_5d(sa, &mapA, full_bar(stage), kc * 64, pt.w0 + p.tap_dw[tap], pt.h0 + p.tap_dh[tap],
-                          p.tap_plane[tap], pt.n0);
+              tma_load_5d(sa, &mapA, full_bar(stage), kc * 64, act_cw(pt.w0 + p.tap_dw[tap], p.tap_plane[tap], p.a_es),
+                          act_ch(pt.h0 + p.tap_dh[tap], p.tap_plane[tap], p.a_es), act_cp(p.tap_plane[tap], p.a_es), pt.n0);
               tma_load_5d(sa + kStageA, &mapB, full_bar(stage), kc * 64, brow0 + p.tap_brow[tap], 0, 0, 0);
             }
             __syncwarp();
@@ -145,16 +145,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int tap0 = p.tap_pairs ? rt.tap * 2 : rt.tap;
 #pragma unroll
             for (int b = 0; b < 2; ++b)
-              tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, pt.w0, pt.h0, p.tap_plane_a[tap0],
-                          pt.n0);
+              tma_load_5d(sa + b * 8192, &mapA, full_bar(stage), rt.mt * 128 + b * 64, act_cw(pt.w0, p.tap_plane_a[tap0], p.a_es),
+                          act_ch(pt.h0, p.tap_plane_a[tap0], p.a_es), act_cp(p.tap_plane_a[tap0], p.a_es), pt.n0);
 #pragma unroll
             for (int b = 0; b < BLOCK_N / 64; ++b) {
               // tap_pairs: boxes 0,1 = tap 2g (channels 0-63, 64-127), boxes 2,3 = tap 2g+1 (the last odd tap is loaded
               // twice; its duplicate columns are dropped by the epilogue)
               const int tap = p.tap_pairs ? min(tap0 + (b >> 1), p.ntaps - 1) : tap0;
               const int c0 = p.tap_pairs ? (b & 1) * 64 : rt.nt * BLOCK_N + b * 64;
-              tma_load_5d(sa + kStageA + b * 8192, &mapB, full_bar(stage), c0, pt.w0 + p.tap_dw[tap],
-                          pt.h0 + p.tap_dh[tap], p.tap_plane[tap], pt.n0);
+              tma_load_5d(sa + kStageA + b * 8192, &mapB, full_bar(stage), c0,
+                          act_cw(pt.w0 + p.tap_dw[tap], p.tap_plane[tap], p.b_es),
+                          act_ch(pt.h0 + p.tap_dh[tap], p.tap_plane[tap], p.b_es), act_cp(p.tap_plane[tap], p.b_es), pt.n0);
             }
           }
           __syncwarp();
@@ -307,7 +308,7 @@ EncodeTiledFn get_encode() {
 }  // namespace
 
 int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int P, int N, int box_c, int box_w, int box_h,
-                 int box_n) {
+                 int box_n, int es) {
   // the encode is a driver-API call: autograd's backward threads may not have bound the primary context yet
   static thread_local bool ctx_bound = false;
   if (!ctx_bound) {
@@ -322,8 +323,12 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int P, i
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)P, (cuuint64_t)N};
   cuuint64_t s1 = (cuuint64_t)C * 2, s2 = s1 * W, s3 = s2 * H, s4 = s3 * P;
   cuuint64_t strides[4] = {s1, s2, s3, s4};
-  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u, (cuuint32_t)box_n};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * es), (cuuint32_t)(box_h * es), 1u, (cuuint32_t)box_n};
+  cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+  if (box_w * es > 256 || box_h * es > 256) {
+    vcd_set_error("TMA map: box %d x %d with element stride %d exceeds 256", box_w, box_h, es);
+    return -4;
+  }
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (s1 & 15)) {
     vcd_set_error("TMA map: base/stride not 16-byte aligned (C=%d)", C);
     return -4;

@@ -47,6 +47,7 @@ struct UmmaParams {
   int batches;  // 1 for conv wgrad (all images reduced), Nimg for attention (per-image result)
   // form 1, Nout = 128 only: one BLOCK_N = 256 tile covers TWO taps x 128 input channels (columns 0-127: tap 2g,
   // 128-255: tap 2g+1), so each MMA reads 4 KB of A for 256 columns instead of 128 (shared-memory operand bound)
+  int a_es, b_es;  // TMA element stride (1 | 2) of the A / B activation map: coordinates (w*es + pw, h*es + ph)
   int tap_pairs;
   int tap_items;  // tiles along the tap axis: ntaps, or ceil(ntaps / 2) with tap_pairs
   // descriptor constants
@@ -59,6 +60,9 @@ struct UmmaParams {
 
 int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p, int block_n, cudaStream_t st);
 
-// activation map: dims (C, W, H, P, N); strides derive from a dense [N][P][H][W][C] bf16 tensor
+// activation map: dims (C, W, H, P, N); strides derive from a dense [N][P][H][W][C] bf16 tensor.
+// es = 2: the box samples every second pixel along W and H (TMA element strides), so a coordinate (2*w + pw, 2*h + ph)
+// addresses pixel (w, h) of parity plane (ph, pw) of a plain NHWC tensor — stride-2 convolutions and the phase form of
+// Upsample2D read their operands in place, without a space-to-planes copy.  box_w / box_h count LOADED pixels.
 int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int P, int N, int box_c, int box_w, int box_h,
-                 int box_n);
+                 int box_n, int es = 1);

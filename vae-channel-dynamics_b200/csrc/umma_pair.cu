@@ -192,8 +192,9 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_wait(aempty(sa), pa ^ 1u);
           if (elect_one_sync()) {
             if (rank == 0) mbar_arrive_expect_tx(afull(sa), 2u * p.a_box_bytes);
-            tma_load_5d_pair(a_base + sa * kABytes, &mapA, afull(sa) & kPeerBitMask, kc * 64, tc.w0 + p.g_dw[g],
-                             tc.h0 + p.g_dh[g], p.g_plane[g], tc.n);
+            tma_load_5d_pair(a_base + sa * kABytes, &mapA, afull(sa) & kPeerBitMask, kc * 64,
+                             act_cw(tc.w0 + p.g_dw[g], p.g_plane[g], p.a_es), act_ch(tc.h0 + p.g_dh[g], p.g_plane[g], p.a_es),
+                             act_cp(p.g_plane[g], p.a_es), tc.n);
           }
           __syncwarp();
           if (++sa == C::kAStages) { sa = 0; pa ^= 1u; }
@@ -526,11 +527,14 @@ umma_pair_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * C::kStageBytes);
 #pragma unroll
           for (int b = 0; b < 2; ++b)
-            tma_load_5d_pair(sa + b * 8192, &mapA, lbar, a_c0 + b * 64, w0, h0, p.tap_plane_a[it.tap], n0);
+            tma_load_5d_pair(sa + b * 8192, &mapA, lbar, a_c0 + b * 64, act_cw(w0, p.tap_plane_a[it.tap], p.a_es),
+                             act_ch(h0, p.tap_plane_a[it.tap], p.a_es), act_cp(p.tap_plane_a[it.tap], p.a_es), n0);
 #pragma unroll
           for (int b = 0; b < BLOCK_N / 128; ++b)
-            tma_load_5d_pair(sa + C::kABytes + b * 8192, &mapB, lbar, b_c0 + b * 64, w0 + p.tap_dw[it.tap],
-                             h0 + p.tap_dh[it.tap], p.tap_plane[it.tap], n0);
+            tma_load_5d_pair(sa + C::kABytes + b * 8192, &mapB, lbar, b_c0 + b * 64,
+                             act_cw(w0 + p.tap_dw[it.tap], p.tap_plane[it.tap], p.b_es),
+                             act_ch(h0 + p.tap_dh[it.tap], p.tap_plane[it.tap], p.b_es), act_cp(p.tap_plane[it.tap], p.b_es),
+                             n0);
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -625,6 +629,7 @@ bool pair_enabled() {
 bool pair_setup_halo(PairParams& p, int W, int H, int N, const PairTap* taps, int ntaps, int block_n, int* box_h_out) {
   if (W < 8 || H < 16 || ntaps < 1 || ntaps > 16) return false;
   p.mode = 0;
+  if (p.a_es != 2) p.a_es = 1;
   p.W = W; p.H = H; p.Nimg = N;
   p.tiles_w = (W + 7) / 8;
   p.tiles_h = (H + 15) / 16;
@@ -680,6 +685,7 @@ bool pair_setup_halo(PairParams& p, int W, int H, int N, const PairTap* taps, in
 
 void pair_setup_rows(PairParams& p, int rows, int batch, int pair_in_image, int brow, int block_n) {
   p.mode = 1;
+  p.a_es = 1;
   p.W = rows; p.H = 1; p.Nimg = batch;
   p.tiles_w = (rows + 127) / 128;
   p.tiles_h = 1;
@@ -740,6 +746,8 @@ int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p,
 int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgradParams& p, int block_n, cudaStream_t st) {
   p.total_items = p.ntaps * p.n_tiles * p.m_pairs * p.splits;
   if (p.total_items <= 0) return 0;
+  if (p.a_es != 2) p.a_es = 1;
+  if (p.b_es != 2) p.b_es = 1;
   ++g_pair_launches;
   // kind::f16: D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3, M = 256 >> 4
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(block_n >> 3) << 17) |

@@ -28,6 +28,7 @@ struct PairParams {
   int pairs;             // pair-tiles
   int n_tiles;           // ceil(Nout / BLOCK_N)
   int total_items;       // pairs * n_tiles
+  int a_es;              // TMA element stride of the A map (1 | 2, see make_act_map)
   int box_w;             // A box width in pixels (HALO: 8 + halo_w, ROWS: 128)
   uint32_t a_box_bytes;  // bytes of one A box
   int ngroups;           // A boxes per K chunk (one per tensor plane the taps touch)
@@ -92,6 +93,7 @@ struct PairWgradParams {
   int tiles_w, tiles_h, tiles_n;
   int ntaps;
   int tap_dw[16], tap_dh[16], tap_plane[16], tap_plane_a[16];
+  int a_es, b_es;                 // TMA element strides of the A (dy) and B (x) maps
   int m_pairs;                    // Cout / 256
   int n_tiles;                    // Cin / BLOCK_N
   int splits, k_per_split, k_tiles;

@@ -94,6 +94,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+// activation-map coordinates of pixel (w, h) of parity plane `plane` = ph*2 + pw: with element stride es = 2 the map
+// covers the plain NHWC tensor and the plane is the coordinate parity; with es = 1 the plane is the 4th coordinate
+__device__ __forceinline__ int act_cw(int w, int plane, int es) { return es == 2 ? 2 * w + (plane & 1) : w; }
+__device__ __forceinline__ int act_ch(int h, int plane, int es) { return es == 2 ? 2 * h + (plane >> 1) : h; }
+__device__ __forceinline__ int act_cp(int plane, int es) { return es == 2 ? 0 : plane; }
+
 // ---------------------------------------------------------------- CTA-pair (cta_group::2) variants
 // A shared::cta address is also a valid shared::cluster address of the executing CTA; clearing bit 24 names the
 // same offset in the even (leader) CTA of the pair.

@@ -204,10 +204,6 @@ class _ConvFn(torch.autograd.Function):
         umma = impl != IMPL_SIMT and _lib.lib().vcd_conv_umma_supported(Cin, Cout, KH, KW, stride) == 1
         planes = 0
         xs = x
-        if stride == 2 and umma:
-            xs = torch.empty((N, 4, H // 2, W // 2, Cin), dtype=torch.bfloat16, device=x.device)
-            call("vcd_space_to_planes", _p(x), _p(xs), N, H, W, Cin, _st())
-            planes = 1
         if residual is not None:
             residual = _nhwc(residual)
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
@@ -237,13 +233,7 @@ class _ConvFn(torch.autograd.Function):
         wf, wd, _ = ctx.packs.current()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            if planes:
-                dxp = torch.empty((N, 4, H // 2, W // 2, Cin), dtype=torch.bfloat16, device=dy.device)
-                call("vcd_conv2d_dgrad", _p(dy), _p(wf), _p(wd), _p(dxp), None, N, H, W, Cin, Cout, KH, KW, stride, pad_t,
-                     pad_l, Ho, Wo, 1, impl, _st())
-                dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
-                call("vcd_planes_to_space", _p(dxp), _p(dx), N, H, W, Cin, _st())
-            elif ctx.gn_info is not None:
+            if ctx.gn_info is not None:
                 gx, gsums, ggamma, gbeta, geps, gact, ggroups = ctx.gn_info
                 dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
                 dsdb = torch.empty(N * Cin * 2, dtype=torch.float32, device=dy.device)
@@ -339,8 +329,7 @@ class _UpConvFn(torch.autograd.Function):
         dy = _nhwc(dy)
         wf, wd, _ = ctx.packs.current()
         colsum = pop_colsum(dy) if bias is not None else None
-        dyp = torch.empty((N, 4, H, W, Cout), dtype=torch.bfloat16, device=dy.device)
-        call("vcd_space_to_planes", _p(dy), _p(dyp), N, 2 * H, 2 * W, Cout, _st())
+        dyp = dy   # the phase kernels read the parity planes of dy in place (element-strided TMA maps)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
