@@ -111,6 +111,10 @@ int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw, void* db,
 /* Number of launches of the CTA-pair (tcgen05.mma.cta_group::2, halo-reuse) kernel since the library was loaded:
  * lets tests and the bench assert that the pair path, not the single-CTA kernel, served a layer. */
 int64_t vcd_pair_kernel_launches(void);
+/* Route the GEMM-path layers through the CTA-pair kernels (default, 1) or the single-CTA tcgen05 kernel (0): two
+ * independent device implementations of the same arithmetic, compared against each other at full layer sizes by
+ * tests/test_fullsize_gpu.py.  Returns the previous setting.  Env VCD_PAIR=0 sets the initial value. */
+int vcd_set_pair_kernels(int enabled);
 
 /* NHWC [N][H][W][C] <-> parity planes [N][2][2][H/2][W/2][C] (stride-2 convs), H and W even */
 int vcd_space_to_planes(const void* x, void* xp, int N, int H, int W, int C, vcd_stream_t stream);

@@ -45,8 +45,8 @@ def _oracle_autocast_step(oracle, x, noise):
     return out["reconstruction"].detach().float(), out["latent_dist"].mean.detach().float(), float(rec), float(kl), grads
 
 
-@pytest.mark.parametrize("impl", ["simt", "auto"])
-def test_forward_backward_matches_oracle(vcd, pair, monkeypatch, impl):
+@pytest.mark.parametrize("impl,R,B", [("simt", 64, 2), ("auto", 64, 2), ("auto", 256, 1)])
+def test_forward_backward_matches_oracle(vcd, pair, monkeypatch, impl, R, B):
     """Three-way comparison on identical weights, pixels and noise:
          truth = oracle in fp32;  ref16 = oracle under bf16 autocast (the reference's bf16 path);  ours.
     Gate: our deviation from the fp32 truth may not exceed 1.5x the deviation the reference's own bf16 path
@@ -56,7 +56,9 @@ def test_forward_backward_matches_oracle(vcd, pair, monkeypatch, impl):
     vcd.ops.set_conv_impl(vcd._lib.IMPL_SIMT if impl == "simt" else vcd._lib.IMPL_AUTO)
     try:
         torch.manual_seed(7)
-        R, B = 64, 2
+        # R = 256: every level is >= 32 x 32, so all convs run on the CTA-pair halo kernel (umma_pair.cu), the
+        # upsamplers as phase convolutions, the downsamplers through element-strided TMA maps
+        n_pair0 = vcd._lib.lib().vcd_pair_kernel_launches()
         x = torch.rand(B, 3, R, R, device="cuda") * 2 - 1
         noise = torch.randn(B, 4, R // 8, R // 8, device="cuda")
         r16_rec, r16_mean, r16_recl, r16_kl, r16_g = _oracle_autocast_step(oracle, x, noise)
@@ -92,6 +94,8 @@ def test_forward_backward_matches_oracle(vcd, pair, monkeypatch, impl):
         assert float(e_ours.median()) < 1.5 * float(e_ref.median()) + 5e-3, (float(e_ours.median()), float(e_ref.median()))
         assert float(e_ours.max()) < 1.5 * float(e_ref.max()) + 2e-2, (float(e_ours.max()), float(e_ref.max()))
         assert float(e_ours.median()) < 5e-2
+        if impl == "auto" and R >= 256:
+            assert vcd._lib.lib().vcd_pair_kernel_launches() - n_pair0 >= 150
     finally:
         vcd.ops.set_conv_impl(vcd._lib.IMPL_AUTO)
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     "vcd_upconv2d_wgrad_ws_bytes": (_i64, [_i, _i]),
     "vcd_upconv2d_wgrad": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     "vcd_pair_kernel_launches": (_i64, []),
+    "vcd_set_pair_kernels": (_i, [_i]),
     "vcd_space_to_planes": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vcd_planes_to_space": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vcd_upsample2x_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),

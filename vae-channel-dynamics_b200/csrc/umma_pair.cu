@@ -617,13 +617,18 @@ uint32_t pair_idesc(int n) {
 
 }  // namespace
 
+static int g_pair_on = -1;
 bool pair_enabled() {
-  static int on = -1;
-  if (on < 0) {
+  if (g_pair_on < 0) {
     const char* e = getenv("VCD_PAIR");
-    on = (e && e[0] == '0') ? 0 : 1;
+    g_pair_on = (e && e[0] == '0') ? 0 : 1;
   }
-  return on == 1;
+  return g_pair_on == 1;
+}
+extern "C" int vcd_set_pair_kernels(int enabled) {
+  const int prev = pair_enabled() ? 1 : 0;
+  g_pair_on = enabled ? 1 : 0;
+  return prev;
 }
 
 bool pair_setup_halo(PairParams& p, int W, int H, int N, const PairTap* taps, int ntaps, int block_n, int* box_h_out) {
