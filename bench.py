@@ -309,7 +309,7 @@ def gn_roofline(torch, vcd, R, B, peaks):
             _st())),
         "gn_bwd_apply(+skip gradient, +bias-gradient column sums)": (8, lambda i: call(
             "vcd_gn_bwd_apply", _p(xs[i % n]), _p(gs[i % n]), _p(sums), _p(gamma), _p(beta), pdt, _p(dsdb), _p(out),
-            _p(gs[(i + 1) % n]), _p(colsum), 1e-6, 1, B, hw, C, 32, _st())),
+            _p(gs[(i + 1) % n]), _p(colsum), None, None, 1e-6, 1, B, hw, C, 32, _st())),
     }
     peak = peaks.get("hbm_gbs", 6650.0)
     res = []

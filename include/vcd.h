@@ -148,9 +148,12 @@ int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* sums, const
 /* dx = GroupNorm/SiLU backward (+ dres, the gradient arriving over the block's skip connection, may be NULL);
  * dx_colsum (fp32 [C], may be NULL) receives the per-channel sums of dx = the bias gradient of the conv that
  * produced x */
+/* dgamma / dbeta ([C], parameter dtype, may both be NULL): when given, the kernel's first block also writes the
+ * parameter gradients (the arithmetic of vcd_gn_param_grad), saving that launch. */
 int vcd_gn_bwd_apply(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
                      int param_dtype, const float* dsdb, void* dx, const void* dres, float* dx_colsum,
-                     float eps, int act_silu, int N, int HW, int C, int G, vcd_stream_t stream);
+                     void* dgamma, void* dbeta, float eps, int act_silu, int N, int HW, int C, int G,
+                     vcd_stream_t stream);
 int vcd_gn_param_grad(const double* sums, const float* dsdb, void* dgamma, void* dbeta, int param_dtype,
                       float eps, int N, int HW, int C, int G, vcd_stream_t stream);
 /* stand-alone SiLU (only used when a foreign forward hook needs the pre-activation tensor) */

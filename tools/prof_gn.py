@@ -39,9 +39,9 @@ for sh in a.shapes:
         "bwd_reduce": (lambda i: call("vcd_gn_bwd_reduce", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(sums), _p(gamma), _p(beta),
                                       pdt, _p(dsdb), 1e-6, 1, B, hw, C, 32, _st()), 4),
         "bwd_apply": (lambda i: call("vcd_gn_bwd_apply", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(sums), _p(gamma), _p(beta), pdt,
-                                     _p(dsdb), _p(out), None, _p(colsum), 1e-6, 1, B, hw, C, 32, _st()), 6),
+                                     _p(dsdb), _p(out), None, _p(colsum), None, None, 1e-6, 1, B, hw, C, 32, _st()), 6),
         "bwd_apply+res": (lambda i: call("vcd_gn_bwd_apply", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(sums), _p(gamma), _p(beta),
-                                         pdt, _p(dsdb), _p(out), _p(rs[i % nbuf]), _p(colsum), 1e-6, 1, B, hw, C, 32, _st()), 8),
+                                         pdt, _p(dsdb), _p(out), _p(rs[i % nbuf]), _p(colsum), None, None, 1e-6, 1, B, hw, C, 32, _st()), 8),
     }
     line = []
     for name, (fn, bpe) in fns.items():

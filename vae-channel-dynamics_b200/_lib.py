@@ -44,7 +44,7 @@ SIGNATURES = {
     "vcd_gn_stats": (_i, [_p, _p, _p, _f, _i, _i, _i, _i, _p]),
     "vcd_gn_apply_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _f, _f, _i, _i, _i, _i, _i, _p]),
     "vcd_gn_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _i, _i, _i, _i, _i, _p]),
-    "vcd_gn_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p]),
+    "vcd_gn_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p]),
     "vcd_gn_param_grad": (_i, [_p, _p, _p, _p, _i, _f, _i, _i, _i, _i, _p]),
     "vcd_silu_fwd": (_i, [_p, _p, _i64, _p]),
     "vcd_silu_bwd": (_i, [_p, _p, _p, _i64, _p]),

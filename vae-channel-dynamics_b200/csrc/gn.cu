@@ -294,8 +294,9 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_kernel(const bf16* _
                                                                 const void* __restrict__ beta, int pdt,
                                                                 const float* __restrict__ dsdb, bf16* __restrict__ dx,
                                                                 const bf16* __restrict__ dres,
-                                                                float* __restrict__ colsum, float eps, int act, int HW,
-                                                                int C, int G, int ppb) {
+                                                                float* __restrict__ colsum, void* __restrict__ dgamma,
+                                                                void* __restrict__ dbeta, int N, float eps, int act,
+                                                                int HW, int C, int G, int ppb) {
   extern __shared__ float sm[];  // [1][8][PL][V] when colsum
   constexpr int kU = 2;          // fewer pixels in flight than the other passes: three streams per pixel
   const int n = blockIdx.y;
@@ -390,6 +391,26 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_kernel(const bf16* _
     deposit<1>(sm, m, acc);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kThreads) atomicAdd(&colsum[c], lane_sum(sm, m, 0, c));
+  }
+  // parameter gradients (vcd_gn_param_grad's arithmetic) by the first block: they need only sums and dsdb, complete
+  // before this kernel started — one launch less per layer
+  if (dgamma && blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      const int g = c / D;
+      float dg = 0.f, dbv = 0.f;
+      for (int i = 0; i < N; ++i) {
+        const double sg = sums[((int64_t)i * G + g) * 2], qg = sums[((int64_t)i * G + g) * 2 + 1];
+        const double mu = sg / cnt;
+        double var = qg / cnt - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float ds = dsdb[((int64_t)i * C + c) * 2], db = dsdb[((int64_t)i * C + c) * 2 + 1];
+        dg += (ds - mean * db) * rstd;
+        dbv += db;
+      }
+      store_param(dgamma, pdt, c, dg);
+      store_param(dbeta, pdt, c, dbv);
+    }
   }
 }
 
@@ -522,7 +543,8 @@ extern "C" int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* 
 
 extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
                                 int param_dtype, const float* dsdb, void* dx, const void* dres, float* dx_colsum,
-                                float eps, int act_silu, int N, int HW, int C, int G, vcd_stream_t stream) {
+                                void* dgamma, void* dbeta, float eps, int act_silu, int N, int HW, int C, int G,
+                                vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
   if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, as_stream(stream)));
   const size_t smem = dx_colsum ? 8 * kThreads * sizeof(float) : 0;
@@ -530,11 +552,11 @@ extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* s
   if (dres)
     gn_bwd_apply_kernel<true><<<sh.grid, kThreads, smem, as_stream(stream)>>>(
         (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum,
-        eps, act_silu, HW, C, G, sh.ppb);
+        dgamma, dbeta, N, eps, act_silu, HW, C, G, sh.ppb);
   else
     gn_bwd_apply_kernel<false><<<sh.grid, kThreads, smem, as_stream(stream)>>>(
-        (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, nullptr, dx_colsum, eps,
-        act_silu, HW, C, G, sh.ppb);
+        (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, nullptr, dx_colsum, dgamma, dbeta,
+        N, eps, act_silu, HW, C, G, sh.ppb);
   VCD_LAUNCH_CHECK();
   return 0;
 }

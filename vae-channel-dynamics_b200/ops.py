@@ -402,15 +402,16 @@ class _GroupNormFn(torch.autograd.Function):
             dsdb = torch.empty(N * C * 2, dtype=torch.float32, device=x.device)
             call("vcd_gn_bwd_reduce", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), eps, act, N, hw, C, G, _st())
         dx = None
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(beta)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             colsum = torch.empty(C, dtype=torch.float32, device=x.device)
             call("vcd_gn_bwd_apply", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), _p(dx), _p(dres),
-                 _p(colsum), eps, act, N, hw, C, G, _st())
+                 _p(colsum), _p(dgamma), _p(dbeta), eps, act, N, hw, C, G, _st())   # also writes dgamma / dbeta
             push_colsum(dx, colsum)
-        dgamma = torch.empty_like(gamma)
-        dbeta = torch.empty_like(beta)
-        call("vcd_gn_param_grad", _p(sums), _p(dsdb), _p(dgamma), _p(dbeta), pdt, eps, N, hw, C, G, _st())
+        else:
+            call("vcd_gn_param_grad", _p(sums), _p(dsdb), _p(dgamma), _p(dbeta), pdt, eps, N, hw, C, G, _st())
         return dx, dgamma, dbeta, None, None, None, None, None, None, None
 
 
