@@ -1,4 +1,4 @@
-"""Summarise an `ncu --set full` report for profiles/: per-launch key metrics as CSV + the JSON bench.py reads for
+"""Summarise an `ncu --set full` report (or its `--page raw --csv` export) for profiles/: per-launch key metrics as CSV + the JSON bench.py reads for
 roofline.traffic.
   python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_ncu_conv [dominant-kernel-regex]"""
 import csv
@@ -10,7 +10,10 @@ import sys
 
 rep, out = sys.argv[1], sys.argv[2]
 dom = re.compile(sys.argv[3] if len(sys.argv) > 3 else r"umma_pair_kernel<256")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):      # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv > x_raw.csv
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 want = ["ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second",

@@ -66,7 +66,7 @@ for sh in a.shapes:
     if k == 3 and lib.vcd_conv2d_dgrad_gn_supported(B, h, h, ci, co, k, k, 1):
         passes.append(("dgrad+gn", dgrad_gn))
     for name, fn in passes:
-        for i in range(2):
+        for i in range(int(os.environ.get('VCD_PROF_WARM', '2'))):
             fn(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()

@@ -45,7 +45,7 @@ for sh in a.shapes:
     }
     line = []
     for name, (fn, bpe) in fns.items():
-        for i in range(2):
+        for i in range(int(os.environ.get('VCD_PROF_WARM', '2'))):
             fn(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
