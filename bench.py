@@ -420,19 +420,45 @@ def main():
 
     def timed(K, e2e):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if os.environ.get("VCD_BENCH_NOGC"):
+            import gc
+            gc.collect()
+            gc.disable()
         barrier()
         l0 = vcd_b200._lib.launches
         e0.record()
         last = None
+        trace = [] if os.environ.get("VCD_BENCH_TRACE") else None
+        cpu_ms = []
+        ends = []
         for i in range(K):
+            # the host never runs more than one step ahead of the device (train.py reads three loss scalars with
+            # .item() every step, train.py:295-297, so the real loop cannot either); without this bound an occasional
+            # full launch queue at the monitor/nudge step produced 100-250 ms outliers
+            if i >= 2:
+                ends[i - 2].synchronize()
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                trace.append(ev)
+            t_cpu0 = time.perf_counter()
             if e2e:
                 x = host[i % n_host].to(dev, non_blocking=True)   # H2D from pinned memory inside the timed region
                 last = float(train_step(x).detach().float().cpu())  # D2H read of the step's loss
             else:
                 last = train_step(resident[i % n_host])
+            if trace is not None:
+                cpu_ms.append((time.perf_counter() - t_cpu0) * 1e3)
+            ends.append(torch.cuda.Event())
+            ends[-1].record()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if trace is not None and rank == 0:
+            per = [trace[i].elapsed_time(trace[i + 1]) for i in range(K - 1)] + [trace[-1].elapsed_time(e1)]
+            print(f"[trace] {'e2e' if e2e else 'resident'} phase: {ms / K:.2f} ms/step over {K} steps: "
+                  + " ".join(f"{t:.0f}" for t in per) + " | host ms/step: " + " ".join(f"{t:.0f}" for t in cpu_ms),
+                  file=sys.stderr)
         launches_per_step[0] = (vcd_b200._lib.launches - l0) / K + (graphed.launches_per_replay if graphed is not None else 0)
         if world > 1:
             t = torch.tensor([ms], device=dev)
