@@ -24,6 +24,7 @@ constexpr int kThreads = 384;    // warps 0-2: TMA / MMA / TMEM alloc, warp 3 id
 constexpr int kEpiWarps = 8;
 constexpr int kABytes = 23552;  // (8+2) x (16+2) rows x 128 B = 23040, rounded up to a multiple of 1024
 constexpr int kBStages = 8;
+constexpr int kStoreSlabBytes = 2048;          // per epilogue warp: 32 rows x 64 B staging for full-sector global stores
 constexpr int kChanAccBytes = 512 * 2 * 4;  // per-channel (sum g*x, sum g) of the fused GroupNorm backward, <= 512 channels
 
 template <int BLOCK_N>
@@ -31,10 +32,11 @@ struct PCfg {
   static constexpr int kTapBytes = (BLOCK_N / 2) * 128;  // this CTA's half of one tap's B rows, 64 K-elements each
   static constexpr int kTapsPerStage = 256 / BLOCK_N;    // a B stage is always 16 KB: 512 MMA cycles per barrier wait
   static constexpr int kBBytes = kTapBytes * kTapsPerStage;
-  static constexpr int kAStages = (BLOCK_N == 256) ? 3 : 4;
+  static constexpr int kAStages = 3;
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kSmemBytes =
-      kAStages * kABytes + kBStages * kBBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kChanAccBytes;
+      kAStages * kABytes + kBStages * kBBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kChanAccBytes +
+      kEpiWarps * kStoreSlabBytes;
 };
 
 struct TileCoord {
@@ -137,6 +139,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   auto tempty = [&](int s) { return bar_base + 8u * (2 * C::kAStages + 2 * kBStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::kAStages + 2 * kBStages + 4);
   float* chan_acc = reinterpret_cast<float*>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));  // [Nout][2]
+  const uint32_t slab_base = bar_base + 512u + kChanAccBytes;  // kEpiWarps x kStoreSlabBytes
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -310,6 +313,12 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       };
       side_load(chalf * (BLOCK_N / 64), sb[0]);
+      // transposed store (see process_chunk): in store instruction i lane l writes 16 B of row 8i + l/4
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      long long off_t[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) off_t[i] = __shfl_sync(0xffffffffu, off, 8 * i + (lane >> 2));
+      const uint32_t slab = slab_base + (uint32_t)(warp - 4) * kStoreSlabBytes;
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       // one 32-column chunk; `cur` holds the chunk's side input (residual or GroupNorm input), already loaded
@@ -318,6 +327,9 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tmem_ld32(taddr + ch * 32, r);
         tmem_wait_ld();
         const int col0 = nt * BLOCK_N + ch * 32;
+        // full chunk of an 8-element-aligned tensor: the 32 x 64 B block goes through shared memory so that every
+        // global store instruction writes 8 rows x 64 contiguous bytes (whole sectors) instead of 32 rows x 16 B
+        const bool staged = (p.Nout & 7) == 0 && col0 + 32 <= p.Nout && !(p.dbg & 16);
         float gv[GNB ? 1 : 16];
         if (!GNB) {
 #pragma unroll
@@ -367,15 +379,27 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
             }
           }
-          bf16* op = p.out + off + ch * 32;
-          if ((p.Nout & 7) == 0) {
+          if (staged) {
+            // this lane's row (64 B) -> the warp's staging slab, 16-byte chunk c at slot c ^ ((lane >> 1) & 3): both
+            // this write and the transposed read below are bank-conflict free
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (col0 + g * 8 < p.Nout) st8(op + g * 8, pack8(v + g * 8));
+            for (int g = 0; g < 4; ++g) {
+              const bf16x8 pk = pack8(v + g * 8);
+              const uint32_t a = slab + (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) * 16);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk.u.x), "r"(pk.u.y), "r"(pk.u.z), "r"(pk.u.w)
+                           : "memory");
+            }
           } else {
+            bf16* op = p.out + off + ch * 32;
+            if ((p.Nout & 7) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.Nout) op[j] = __float2bfloat16_rn(v[j]);
+              for (int g = 0; g < 4; ++g)
+                if (col0 + g * 8 < p.Nout) st8(op + g * 8, pack8(v + g * 8));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.Nout) op[j] = __float2bfloat16_rn(v[j]);
+            }
           }
           if constexpr (!GNB) {
             if (p.gn_sums) {
@@ -387,6 +411,22 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) xs[j] *= v[j];
           }
+        }
+        if (staged && tc.valid && !(p.dbg & 4)) {  // warp-uniform
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2), c = lane & 3;
+            uint32_t x0, x1, x2, x3;
+            const uint32_t a = slab + (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) * 16);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(a) : "memory");
+            if ((vmask >> r) & 1u) {
+              bf16x8 o;
+              o.u = make_uint4(x0, x1, x2, x3);
+              st8(p.out + off_t[i] + ch * 32 + c * 8, o);
+            }
+          }
+          __syncwarp();
         }
         if constexpr (GNB) {
           if (tc.valid && col0 < p.Nout) {  // warp-uniform
