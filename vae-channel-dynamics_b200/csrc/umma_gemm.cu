@@ -59,7 +59,8 @@ struct Cfg {
   static constexpr int kStageBytes = kStageA + kStageB;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kRedSlabBytes = 4096;  // per epilogue warp: staging of the transposed fp32 reduction (form 1)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * kRedSlabBytes;
 };
 
 template <int BLOCK_N>
@@ -267,7 +268,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int tap = p.tap_pairs ? rt.tap * 2 + (ch >> 2) : rt.tap;
           const int col0 = p.tap_pairs ? (ch & 3) * 32 : rt.nt * BLOCK_N + ch * 32;
           float* op = p.acc + (((long long)rt.batch * p.ntaps + tap) * p.Mout + rt.mt * 128 + row) * (long long)p.Nout + col0;
-          if (rt.mt * 128 + row < p.Mout && tap < p.ntaps) {
+          if ((p.Nout & 3) == 0 && col0 + 32 <= p.Nout) {
+            if (tap < p.ntaps) {  // warp-uniform
+              const int row0 = rt.mt * 128 + q * 32;
+              float* op0 = p.acc + (((long long)rt.batch * p.ntaps + tap) * p.Mout + row0) * (long long)p.Nout + col0;
+              red_chunk_32x32(r, bar_base + 256u + (uint32_t)q * C::kRedSlabBytes, op0, p.Nout, p.Mout - row0, lane);
+            }
+          } else if (rt.mt * 128 + row < p.Mout && tap < p.ntaps) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.Nout) atomicAdd(op + j, __uint_as_float(r[j]));

@@ -482,9 +482,10 @@ struct WCfg {
   static constexpr int kABytes = 16384;                 // 128 output channels x 64 pixels (2 boxes)
   static constexpr int kBBytes = (BLOCK_N / 2) * 128;   // this CTA's half of the input channels x 64 pixels
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 6 : 8;
+  static constexpr int kStages = (BLOCK_N == 256) ? 5 : 7;
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+  static constexpr int kRedSlabBytes = 4096;   // per epilogue warp: 32 x 32 fp32 staging for the transposed reduction
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512 + kEpiWarps * kRedSlabBytes;
 };
 struct WItem {
   int tap, nt, mp, k0, nk;
@@ -622,13 +623,18 @@ umma_pair_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       const int co = it.mp * 256 + rank * 128 + row;
+      const int co0 = it.mp * 256 + rank * 128 + q * 32;   // first row of this warp
       float* op = p.acc + ((long long)it.tap * p.Mout + co) * (long long)p.Nout + it.nt * BLOCK_N;
+      float* op0 = p.acc + ((long long)it.tap * p.Mout + co0) * (long long)p.Nout + it.nt * BLOCK_N;
+      const uint32_t slab = bar_base + 512u + (uint32_t)(warp - 4) * C::kRedSlabBytes;
 #pragma unroll 1
       for (int ch = chalf * (BLOCK_N / 64); ch < (chalf + 1) * (BLOCK_N / 64); ++ch) {
         uint32_t r[32];
         tmem_ld32(taddr + ch * 32, r);
         tmem_wait_ld();
-        if (co < p.Mout) {
+        if ((p.Nout & 3) == 0 && it.nt * BLOCK_N + ch * 32 + 32 <= p.Nout) {
+          red_chunk_32x32(r, slab, op0 + ch * 32, p.Nout, p.Mout - co0, lane);
+        } else if (co < p.Mout) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (it.nt * BLOCK_N + ch * 32 + j < p.Nout) atomicAdd(op + ch * 32 + j, __uint_as_float(r[j]));

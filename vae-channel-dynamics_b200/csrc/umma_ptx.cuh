@@ -94,6 +94,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+// ---------------------------------------------------------------- transposed fp32 reduction of one 32 x 32 accumulator chunk
+// `r` holds this lane's row (32 fp32 columns).  The rows go through a 4 KB per-warp shared-memory slab (16-byte slots
+// XOR-swizzled by the row: conflict free both ways) so that each red.global.add.v4.f32 instruction adds 4 rows x 128
+// contiguous bytes — 4 L2 lines per instruction instead of 32 lines per scalar RED.
+//   dst_row0: address of (row 0, column 0) of the chunk; row_stride in floats; rows_valid: rows [0, rows_valid) exist
+__device__ __forceinline__ void red_chunk_32x32(const uint32_t* r, uint32_t slab, float* dst_row0, long long row_stride,
+                                                int rows_valid, int lane) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t a = slab + (uint32_t)lane * 128u + (uint32_t)((g ^ (lane & 7)) * 16);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]),
+                 "r"(r[4 * g + 3])
+                 : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + (lane >> 3), c = lane & 7;
+    float x0, x1, x2, x3;
+    const uint32_t a = slab + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) * 16);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(a) : "memory");
+    if (row < rows_valid) {
+      float* d = dst_row0 + (long long)row * row_stride + c * 4;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
+    }
+  }
+  __syncwarp();
+}
+
 // activation-map coordinates of pixel (w, h) of parity plane `plane` = ph*2 + pw: with element stride es = 2 the map
 // covers the plain NHWC tensor and the plane is the coordinate parity; with es = 1 the plane is the 4th coordinate
 __device__ __forceinline__ int act_cw(int w, int plane, int es) { return es == 2 ? 2 * w + (plane & 1) : w; }
