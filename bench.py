@@ -511,6 +511,17 @@ def main():
             for i in range(2):
                 train_step(resident[i % n_host])
             torch.cuda.synchronize()
+        # idle time on the device between consecutive kernels, attributed to the kernel that follows the gap
+        evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA],
+                     key=lambda e: e.time_range.start)
+        gaps = {}
+        for a, b in zip(evs, evs[1:]):
+            g = b.time_range.start - a.time_range.end
+            if g > 0:
+                k = (a.name[:48], b.name[:48])
+                c = gaps.setdefault(k, [0, 0.0])
+                c[0] += 1
+                c[1] += g
         rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
         tot = sum(e.device_time_total for e in rows)
         with open(args.kernel_table, "w") as f:
@@ -518,6 +529,11 @@ def main():
             f.write(f"{'ms/step':>9} {'share':>6} {'n/step':>7}  kernel\n")
             for e in rows[:45]:
                 f.write(f"{e.device_time_total / 2e3:9.3f} {100 * e.device_time_total / tot:5.1f}% {e.count / 2:7.1f}  {e.key[:110]}\n")
+            gtot = sum(v[1] for v in gaps.values())
+            f.write(f"\nidle gaps between consecutive device activities: {gtot / 2e3:.2f} ms per step\n")
+            f.write(f"{'ms/step':>9} {'n/step':>7} {'us each':>8}  previous -> next\n")
+            for k, v in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
+                f.write(f"{v[1] / 2e3:9.3f} {v[0] / 2:7.1f} {v[1] / v[0]:8.1f}  {k[0]} -> {k[1]}\n")
 
     roof = roof_hbm = cpu = None
     if rank == 0 and not args.no_roofline and not args.quick:
