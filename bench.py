@@ -435,8 +435,9 @@ def main():
             # the host never runs more than one step ahead of the device (train.py reads three loss scalars with
             # .item() every step, train.py:295-297, so the real loop cannot either); without this bound an occasional
             # full launch queue at the monitor/nudge step produced 100-250 ms outliers
-            if i >= 2:
-                ends[i - 2].synchronize()
+            ahead = int(os.environ.get("VCD_BENCH_AHEAD", "1"))
+            if i >= ahead + 1:
+                ends[i - ahead - 1].synchronize()
             if trace is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
@@ -502,6 +503,9 @@ def main():
     ms, launches, loss = timed(args.steps, e2e=False)
     ms_e2e, _, loss_e2e = (ms, 0, loss) if args.quick else timed(args.steps, e2e=True)
     clk = clocks.stop() if rank == 0 else None
+    if os.environ.get("VCD_BENCH_TRACE") and rank == 0:
+        print("[trace] sm clocks (200 ms samples): " + " ".join(r[0] for r in clocks.rows) + " | power W: "
+              + " ".join(r[2].split(".")[0] for r in clocks.rows if len(r) > 2), file=sys.stderr)
     value = args.steps * B * world / (ms / 1e3)
     value_e2e = args.steps * B * world / (ms_e2e / 1e3)
 

@@ -29,7 +29,9 @@ def get_conv_impl() -> int:
 
 
 def _st() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of the current stream of the current device (torch.cuda.current_stream() builds a Stream object and
+    # costs ~16 us per call — 6 ms of host time per training step)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _p(t: Optional[torch.Tensor]):
