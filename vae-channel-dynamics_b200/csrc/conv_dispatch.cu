@@ -1,6 +1,7 @@
 // conv_dispatch.cu — C-ABI convolution / GEMM entry points: shape checks, TMA tensor maps, tile
 // decomposition and tap tables for the tcgen05 kernel (umma_gemm.cu), SIMT path for small channels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_dispatch.h"
@@ -124,6 +125,13 @@ int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, 
     VCD_CUDA(cudaMemsetAsync(gnb->dsdb, 0, sizeof(float) * 2 * N * Nout, st));
   }
   p.a_es = es;
+  // 128 -> 128 channel 3x3 layers: the CTA's whole weight operand (ntaps * kc boxes of 8 KB) fits beside two A boxes, so it
+  // is loaded once per kernel instead of once per 256-pixel item (VCD_BRES=0 disables, for A/B measurement)
+  {
+    static int bres = -1;
+    if (bres < 0) { const char* e = getenv("VCD_BRES"); bres = (e && e[0] == '0') ? 0 : 1; }
+    p.b_resident = (bres && bn == 128 && p.n_tiles == 1 && ntaps * p.kc * 64 * 128 <= 147456 && p.pairs >= 4 * 74) ? 1 : 0;
+  }
   if ((rc = make_act_map(&mA, act, C, Wa, Ha, P, N, 64, p.box_w, box_h, 1, es))) return rc;
   if ((rc = make_act_map(&mB, wpack, C, wrows, 1, 1, 1, 64, bn / 2, 1, 1))) return rc;
   if ((rc = pair_launch(mA, mB, p, bn, st))) return rc;

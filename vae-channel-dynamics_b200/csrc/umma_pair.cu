@@ -24,6 +24,7 @@ constexpr int kThreads = 384;    // warps 0-2: TMA / MMA / TMEM alloc, warp 3 id
 constexpr int kEpiWarps = 8;
 constexpr int kABytes = 23552;  // (8+2) x (16+2) rows x 128 B = 23040, rounded up to a multiple of 1024
 constexpr int kBStages = 8;
+constexpr int kBResidentBytes = 147456;  // 144 KB: 18 boxes of 64 rows x 128 B (3x3 taps x 2 K chunks, N = 128)
 constexpr int kStoreSlabBytes = 2048;          // per epilogue warp: 32 rows x 64 B staging for full-sector global stores
 constexpr int kChanAccBytes = 512 * 2 * 4;  // per-channel (sum g*x, sum g) of the fused GroupNorm backward, <= 512 channels
 
@@ -128,9 +129,12 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   using C = PCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + C::kAStages * kABytes;
-  const uint32_t bar_base = b_base + kBStages * C::kBBytes;
+  // streaming layout: [A ring: kAStages boxes][B ring: kBStages x 16 KB]; B-resident layout (p.b_resident): [B: ntaps*kc
+  // boxes, <= 144 KB][A ring: 2 boxes] inside the same region
+  const int n_a_stages = p.b_resident ? 2 : C::kAStages;
+  const uint32_t b_base = p.b_resident ? smem_base : smem_base + C::kAStages * kABytes;
+  const uint32_t a_base = p.b_resident ? smem_base + kBResidentBytes : smem_base;
+  const uint32_t bar_base = smem_base + C::kAStages * kABytes + kBStages * C::kBBytes;
   auto afull = [&](int s) { return bar_base + 8u * s; };
   auto aempty = [&](int s) { return bar_base + 8u * (C::kAStages + s); };
   auto bfull = [&](int s) { return bar_base + 8u * (2 * C::kAStages + s); };
@@ -186,6 +190,16 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
+    if (p.b_resident && cluster_id < p.total_items) {
+      if (elect_one_sync()) {
+        if (rank == 0) mbar_arrive_expect_tx(bfull(0), 2u * (uint32_t)(p.ntaps * p.kc * C::kTapBytes));
+        for (int kc = 0; kc < p.kc; ++kc)
+          for (int tap = 0; tap < p.ntaps; ++tap)
+            tma_load_5d_pair(b_base + (uint32_t)((kc * p.ntaps + tap) * C::kTapBytes), &mapB, bfull(0) & kPeerBitMask, kc * 64,
+                             rank * (BLOCK_N / 2) + p.tap_brow[tap], 0, 0, 0);
+      }
+      __syncwarp();
+    }
     for (int item = cluster_id; item < p.total_items; item += n_clusters) {
       const int nt = item % p.n_tiles;
       const TileCoord tc = decode_tile(p, item / p.n_tiles, rank);
@@ -200,7 +214,8 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                              act_cp(p.g_plane[g], p.a_es), tc.n);
           }
           __syncwarp();
-          if (++sa == C::kAStages) { sa = 0; pa ^= 1u; }
+          if (++sa == n_a_stages) { sa = 0; pa ^= 1u; }
+          if (p.b_resident) continue;
           for (int tap = p.g_tap0[g]; tap < p.g_tap0[g + 1]; tap += C::kTapsPerStage) {
             const int nt_here = min(C::kTapsPerStage, p.g_tap0[g + 1] - tap);
             mbar_wait(bempty(sb), pb ^ 1u);
@@ -226,6 +241,10 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint32_t pa = 0, pb = 0, acc_phase = 0;
     const uint32_t a_hi = (uint32_t)((p.mode ? 1024 : p.box_w * 128) >> 4) | (1u << 14) | (2u << 29);
     const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    if (p.b_resident && cluster_id < p.total_items) {
+      mbar_wait(bfull(0), 0u);   // the resident B operand of both CTAs has landed
+      tc_fence_after();
+    }
     for (int item = cluster_id; item < p.total_items; item += n_clusters) {
       mbar_wait(tempty(acc), acc_phase ^ 1u);
       tc_fence_after();
@@ -236,6 +255,26 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_wait(afull(sa), pa);
           tc_fence_after();
           const uint32_t sa_addr = a_base + sa * kABytes;
+          if (p.b_resident) {
+            if (elect_one_sync()) {
+              for (int tap = p.g_tap0[g]; tap < p.g_tap0[g + 1]; ++tap) {
+                const uint32_t a0 = sa_addr + (uint32_t)p.tap_aoff[tap];
+                const uint32_t b0 = b_base + (uint32_t)((kc * p.ntaps + tap) * C::kTapBytes);
+                const uint32_t a_lo = ((a0 >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t b_lo = ((b0 >> 4) & 0x3FFFu) | (1u << 16);
+                umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
+                umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), p.idesc, 1u);
+                umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 4), ((uint64_t)b_hi << 32) | (b_lo + 4), p.idesc, 1u);
+                umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 6), ((uint64_t)b_hi << 32) | (b_lo + 6), p.idesc, 1u);
+                accum = 1u;
+              }
+              umma_commit_pair(aempty(sa));
+            }
+            __syncwarp();
+            accum = 1u;
+            if (++sa == n_a_stages) { sa = 0; pa ^= 1u; }
+            continue;
+          }
           for (int tap = p.g_tap0[g]; tap < p.g_tap0[g + 1]; tap += C::kTapsPerStage) {
             const int nt_here = min(C::kTapsPerStage, p.g_tap0[g + 1] - tap);
             mbar_wait(bfull(sb), pb);
@@ -263,7 +302,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
           if (elect_one_sync()) umma_commit_pair(aempty(sa));
           __syncwarp();
-          if (++sa == C::kAStages) { sa = 0; pa ^= 1u; }
+          if (++sa == n_a_stages) { sa = 0; pa ^= 1u; }
         }
       }
       if (elect_one_sync()) umma_commit_pair(tfull(acc));

@@ -39,6 +39,8 @@ struct PairParams {
   int tap_brow[16];      // B row offset of the tap
   int kc;                // 64-channel K chunks per tap
   int b_batch_rows;      // B row offset per image (batched GEMM); 0 = shared weights
+  int b_resident;        // 1: the whole B operand of this CTA (ntaps * kc boxes, <= 144 KB) is loaded ONCE per kernel and
+                         //    stays in shared memory; only the A halo boxes stream (128 -> 128 channel 3x3 convs)
   bf16* out;
   const bf16* residual;
   const float* bias;
