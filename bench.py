@@ -467,6 +467,12 @@ def main():
             ms = float(t)
         return ms, int(launches_per_step[0] * K), float(last)
 
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation over all GPUs of the node, 1-2 s) holds
+    # driver locks and made the first timed phase 10-25 % slower in ~15 % of the runs when it was started right before it;
+    # only the samples taken during the timed region are reported
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     n_warm = args.warmup if args.quick else max(3, args.warmup)
     for i in range(n_warm):
         train_step(resident[i % n_host])
@@ -497,9 +503,7 @@ def main():
         prev = dt
         if steady:
             break
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.rows.clear()   # keep only the samples of the timed region
     ms, launches, loss = timed(args.steps, e2e=False)
     ms_e2e, _, loss_e2e = (ms, 0, loss) if args.quick else timed(args.steps, e2e=True)
     clk = clocks.stop() if rank == 0 else None
