@@ -447,7 +447,10 @@ def main():
                 x = host[i % n_host].to(dev, non_blocking=True)   # H2D from pinned memory inside the timed region
                 last = float(train_step(x).detach().float().cpu())  # D2H read of the step's loss
             else:
-                last = train_step(resident[i % n_host])
+                # device-resident inputs; the loss scalar is read every step exactly as train.py:295-297 does with
+                # .item() (a free-running host made this phase noisy: 89-105 ms per step run to run, against a stable
+                # 89-91 ms with the per-step read the real loop has anyway)
+                last = float(train_step(resident[i % n_host]).detach().float().cpu())
             if trace is not None:
                 cpu_ms.append((time.perf_counter() - t_cpu0) * 1e3)
             ends.append(torch.cuda.Event())
@@ -504,8 +507,12 @@ def main():
         if steady:
             break
     clocks.rows.clear()   # keep only the samples of the timed region
-    ms, launches, loss = timed(args.steps, e2e=False)
-    ms_e2e, _, loss_e2e = (ms, 0, loss) if args.quick else timed(args.steps, e2e=True)
+    if os.environ.get("VCD_BENCH_ORDER") == "e2e_first" and not args.quick:
+        ms_e2e, _, loss_e2e = timed(args.steps, e2e=True)
+        ms, launches, loss = timed(args.steps, e2e=False)
+    else:
+        ms, launches, loss = timed(args.steps, e2e=False)
+        ms_e2e, _, loss_e2e = (ms, 0, loss) if args.quick else timed(args.steps, e2e=True)
     clk = clocks.stop() if rank == 0 else None
     if os.environ.get("VCD_BENCH_TRACE") and rank == 0:
         print("[trace] sm clocks (200 ms samples): " + " ".join(r[0] for r in clocks.rows) + " | power W: "
@@ -567,6 +574,7 @@ def main():
                        "optimizer": "clip_grad_norm 1.0 + AdamW (torch fused) as in train.py:301-304",
                        "execution": "eager per-op launches (DDP bucketed all-reduce for N>1)" if not args.graph else "forward+loss+backward replayed from one CUDA graph (GraphedVAEStep); clip/AdamW/tracker eager",
                        "l2": "4 distinct input batches rotated; every activation tensor exceeds the 126 MB L2 at this size",
+                       "value_phase": "inputs resident in HBM; loss scalar read back every step (train.py:295-297)",
                        "train_tflop_per_image": fl_img / 1e12,
                        "step_mfu_of_sustained_peak": (value / world) * fl_img / 1e12 / peak_t,
                        "nudges_applied": state["nudged"], "inactive_flagged": state["inactive"], "final_loss": loss},
