@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
     (2, 512, 256, 128, 3, 1),     # decoder.up_blocks.3.resnets.0.conv1
     (2, 512, 256, 128, 1, 1),     # ... and its 1x1 shortcut
     (2, 512, 128, 128, 3, 2),     # encoder.down_blocks.0.downsamplers.0
+    (2, 512, 128, 3, 3, 1),       # decoder.conv_out: narrow N with the weight operand resident in shared memory
 ])
 def test_pair_and_single_cta_kernels_agree_at_full_size(vcd, N, H, cin, cout, k, stride):
     ops, lib = vcd.ops, vcd._lib.lib()
