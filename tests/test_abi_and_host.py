@@ -148,3 +148,29 @@ def test_bench_flop_model_matches_survey():
     assert abs(conv / 1e9 - 3545.3) < 0.1 and abs(attn / 1e9 - 85.9) < 0.1 and abs(total / 1e12 - 10.89) < 0.01
     total, conv, attn = bench.train_flops_per_image(256)
     assert abs(total / 1e12 - 2.685) < 0.001
+
+
+def test_groupnorm_producers_are_marked(vcd):
+    """Every conv / linear whose output is the input of a GroupNorm emits that GroupNorm's sums from its GEMM epilogue
+    (vae.py _mark_groupnorm_producers): conv_in, every resnet conv1, block outputs that feed a norm1 / attention /
+    conv_norm_out, the sampler convs and the attention output projection — but NOT the last resnet of a block that ends
+    in a Down/Upsample2D conv, the 1x1 shortcuts, conv_out or the quant convs."""
+    m = vcd.B200AutoencoderKL()
+    g = m.config["norm_num_groups"]
+    marked = {n for n, mod in m.named_modules() if getattr(mod, "_gn_groups", 0) == g}
+    assert "encoder.conv_in" in marked and "decoder.conv_in" in marked
+    for n, mod in m.named_modules():
+        if n.endswith(".conv1"):
+            assert n in marked, n
+        if n.endswith(".conv_shortcut") or n.endswith("conv_out") or n in ("quant_conv", "post_quant_conv"):
+            assert n not in marked, n
+    assert "encoder.down_blocks.0.resnets.0.conv2" in marked          # feeds resnets.1.norm1
+    assert "encoder.down_blocks.0.resnets.1.conv2" not in marked      # feeds the Downsample2D conv
+    assert "encoder.down_blocks.0.downsamplers.0.conv" in marked      # feeds down_blocks.1.resnets.0.norm1
+    assert "encoder.down_blocks.3.resnets.1.conv2" in marked          # no downsampler: feeds mid_block.resnets.0.norm1
+    assert "decoder.up_blocks.2.resnets.2.conv2" not in marked        # feeds the Upsample2D conv
+    assert "decoder.up_blocks.2.upsamplers.0.conv" in marked
+    assert "decoder.up_blocks.3.resnets.2.conv2" in marked            # feeds decoder.conv_norm_out
+    assert "encoder.mid_block.attentions.0.to_out.0" in marked and "encoder.mid_block.attentions.0.to_q" not in marked
+    # one producer per GroupNorm: 52 GroupNorms, 52 marked producers
+    assert len(marked) == sum(1 for mod in m.modules() if isinstance(mod, nn.GroupNorm))
