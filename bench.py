@@ -524,7 +524,7 @@ def main():
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for i in range(2):
-                train_step(resident[i % n_host])
+                float(train_step(resident[i % n_host]).detach().float().cpu())   # as in the timed region
             torch.cuda.synchronize()
         # idle time on the device between consecutive kernels, attributed to the kernel that follows the gap
         evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA],

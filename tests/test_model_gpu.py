@@ -274,3 +274,33 @@ def test_graphed_step_matches_eager_step(vcd, pair, monkeypatch):
         w.vae.decoder.conv_out.weight.mul_(3.0)
     _, r3, _ = g.step(x)
     assert abs(float(r3) - r2_value) > 1e-3 * r2_value
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_optimizer_step_reaches_the_gemm_operand_packs(vcd, pair, fused):
+    """torch.optim.AdamW(fused=True) updates parameters WITHOUT bumping `_version`; the bf16 GEMM operand packs must be
+    rebuilt anyway: after one optimizer step our forward must equal the oracle's forward on the SAME updated weights
+    (and differ from our forward before the step)."""
+    from oracle.torch_vae import oracle_forward
+    oracle, _ = pair
+    vcd.add_src_to_path()
+    from models.sdxl_vae_wrapper import SDXLVAEWrapper
+    w = SDXLVAEWrapper("random-init:42").cuda()
+    w.vae.load_state_dict(oracle.state_dict())
+    opt = torch.optim.AdamW(w.parameters(), lr=2e-3, weight_decay=0.0, fused=fused)
+    torch.manual_seed(3)
+    x = torch.rand(2, 3, 64, 64, device="cuda") * 2 - 1
+    out = w(x, sample_posterior=False)
+    before = out["reconstruction"].detach().clone()
+    total, _, _ = vcd.vae_loss(out, x, 1e-6)
+    total.backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    after = w(x, sample_posterior=False)["reconstruction"].detach()
+    assert rel_err(after, before) > 5e-2, "the optimizer step did not reach the convolution operands"
+    import copy
+    ref = copy.deepcopy(oracle)
+    ref.load_state_dict(w.vae.state_dict())
+    with torch.no_grad():
+        expect = oracle_forward(ref, x, False)["reconstruction"]
+    assert rel_err(after, expect) < 8e-2

@@ -3,7 +3,7 @@
 Internal activation layout: bf16, NHWC contiguous tensors of shape [N, H, W, C].  Parameters stay
 ordinary ``nn.Parameter``s (fp32 or bf16, diffusers OIHW layout) so the optimizer, DDP, the nudger
 and the dead-weight tracker all see the storage they see in the reference; GEMM operand packs are
-rebuilt from them whenever ``param._version`` changes (i.e. after every optimizer step / nudge).
+rebuilt on every forward (fused optimizers do not bump ``param._version``, so no host-side key can prove a pack current).
 """
 from __future__ import annotations
 
@@ -112,12 +112,18 @@ class PackedWeights:
 
     def __init__(self):
         self.key = None
+        self.frozen = False
         self.wf = self.wd = self.bias = None
 
-    def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+    def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor], training: bool = False):
+        """training: this forward will be differentiated w.r.t. the weights (ctx.needs_input_grad inside the autograd
+        Function — grad mode itself is off there)."""
         key = (weight.data_ptr(), weight._version, weight.dtype, None if bias is None else (bias.data_ptr(), bias._version))
-        # under CUDA-graph capture the pack kernel must be part of the graph: every replay sees updated weights
-        if key != self.key or torch.cuda.is_current_stream_capturing():
+        # EVERY forward repacks (75 small kernels, ~0.4 ms per 512^2 step): fused optimizers (torch.optim.AdamW(fused=True))
+        # and `.data` writes update a parameter without touching `_version`, so no host-side key can prove that the packs
+        # are current — a version-keyed cache left the GEMMs on the weights of the first step.  `frozen` (set by
+        # freeze_weight_packs for inference loops on fixed weights) is the only way to skip the repack.
+        if key != self.key or not self.frozen or training or torch.cuda.is_current_stream_capturing():
             _require_cuda(weight, "conv weight")
             w = weight.detach()
             if not w.is_contiguous():
@@ -137,6 +143,16 @@ class PackedWeights:
     def current(self):
         """the packs of the forward pass (backward never repacks)"""
         return self.wf, self.wd, self.bias
+
+
+def freeze_weight_packs(model: torch.nn.Module, frozen: bool = True) -> None:
+    """Inference on fixed weights: keep the GEMM operand packs of every layer between forwards (they are still rebuilt
+    when a parameter's `_version` changes).  Training code never needs this."""
+    for m in model.modules():
+        for attr in ("_packs", "_up_packs"):
+            pk = getattr(m, attr, None)
+            if pk is not None:
+                pk.frozen = frozen
 
 
 def _workspace(fn: str, shape, impl: int, device):
@@ -202,7 +218,7 @@ class _ConvFn(torch.autograd.Function):
         Cout = weight.shape[0]
         KH, KW = (weight.shape[2], weight.shape[3]) if weight.dim() == 4 else (1, 1)
         Ho, Wo = out_hw
-        wf, wd, b32 = packs.get(weight, bias)
+        wf, wd, b32 = packs.get(weight, bias, training=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         umma = impl != IMPL_SIMT and _lib.lib().vcd_conv_umma_supported(Cin, Cout, KH, KW, stride) == 1
         planes = 0
         xs = x
@@ -275,11 +291,12 @@ class UpconvPackedWeights:
 
     def __init__(self):
         self.key = None
+        self.frozen = False
         self.wf = self.wd = self.bias = None
 
-    def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+    def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor], training: bool = False):
         key = (weight.data_ptr(), weight._version, weight.dtype, None if bias is None else (bias.data_ptr(), bias._version))
-        if key != self.key or torch.cuda.is_current_stream_capturing():
+        if key != self.key or not self.frozen or training or torch.cuda.is_current_stream_capturing():
             _require_cuda(weight, "conv weight")
             w = weight.detach()
             if not w.is_contiguous():
@@ -313,7 +330,7 @@ class _UpConvFn(torch.autograd.Function):
         x = _nhwc(x)
         N, H, W, Cin = x.shape
         Cout = weight.shape[0]
-        wf, wd, b32 = packs.get(weight, bias)
+        wf, wd, b32 = packs.get(weight, bias, training=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         y = torch.empty((N, 2 * H, 2 * W, Cout), dtype=torch.bfloat16, device=x.device)
         sums = torch.empty(N * gn_groups * 2, dtype=torch.float64, device=x.device) if gn_groups else None
         call("vcd_upconv2d_fprop", _p(x), _p(wf), _p(b32), _p(y), N, H, W, Cin, Cout, _p(sums), gn_groups, _st())
