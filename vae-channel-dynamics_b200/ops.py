@@ -168,13 +168,14 @@ _COLSUMS = {}
 
 
 def push_colsum(t: torch.Tensor, colsum: torch.Tensor) -> None:
-    # the entry keeps `t` alive, so its address cannot be recycled for another tensor while the entry exists
-    _COLSUMS[t.data_ptr()] = (t, colsum)
+    # the entry keeps `t` alive, so its address cannot be recycled for another tensor while the entry exists; the version
+    # counter detects an in-place change of `t` after the hand-off (autograd accumulating a second gradient into it)
+    _COLSUMS[t.data_ptr()] = (t, colsum, t._version)
 
 
 def pop_colsum(t: torch.Tensor):
     e = _COLSUMS.pop(t.data_ptr(), None)
-    if e is None or e[0].numel() != t.numel() or e[0].shape[-1] != t.shape[-1]:
+    if e is None or e[0].numel() != t.numel() or e[0].shape[-1] != t.shape[-1] or e[0]._version != e[2]:
         return None
     return e[1]
 
@@ -199,12 +200,12 @@ _GNSUMS = {}
 
 
 def push_gn_sums(t: torch.Tensor, sums: torch.Tensor, groups: int) -> None:
-    _GNSUMS[t.data_ptr()] = (t, sums, groups)
+    _GNSUMS[t.data_ptr()] = (t, sums, groups, t._version)
 
 
 def pop_gn_sums(t: torch.Tensor, groups: int):
     e = _GNSUMS.pop(t.data_ptr(), None)
-    if e is None or e[0].shape != t.shape or e[2] != groups:
+    if e is None or e[0].shape != t.shape or e[2] != groups or e[0]._version != e[3]:   # modified in place since
         return None
     return e[1]
 
@@ -234,9 +235,9 @@ class _ConvFn(torch.autograd.Function):
         # x = act(GroupNorm(.)) with this conv as its only consumer: the dgrad epilogue will do the GroupNorm's reduction
         gi = _GN_FWD.pop(x.data_ptr(), None)
         ctx.gn_info = None
-        if (gi is not None and gi[0].shape == x.shape and umma and
+        if (gi is not None and gi[0].shape == x.shape and gi[0]._version == gi[-1] and umma and
                 _lib.lib().vcd_conv2d_dgrad_gn_supported(N, H, W, Cin, Cout, KH, KW, stride) == 1):
-            ctx.gn_info = gi[1:]
+            ctx.gn_info = gi[1:-1]
         ctx.save_for_backward(xs, weight, bias)
         ctx.packs = packs
         ctx.cfg = (N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl)
@@ -259,7 +260,7 @@ class _ConvFn(torch.autograd.Function):
                 gg, gb = ggamma.detach(), gbeta.detach()
                 call("vcd_conv2d_dgrad_gn", _p(dy), _p(wd), _p(dx), N, H, W, Cin, Cout, KH, KW, pad_t, pad_l, _p(gx), _p(gsums),
                      _p(gg), _p(gb), dtype_code(gg), ggroups, geps, gact, _p(dsdb), _p(ab), _st())
-                _GN_BWD[dx.data_ptr()] = (dx, dsdb)
+                _GN_BWD[dx.data_ptr()] = (dx, dsdb, dx._version)
             else:
                 dx = torch.empty((N, H, W, Cin), dtype=torch.bfloat16, device=dy.device)
                 ws = _workspace("vcd_conv2d_dgrad_ws_bytes", (N, H, W, Cin, Cout, KH, KW, stride), impl, dy.device)
@@ -399,7 +400,7 @@ class _GroupNormFn(torch.autograd.Function):
         ctx.save_for_backward(x, sums, gamma, beta)
         ctx.cfg = (N, hw, C, groups, float(eps), 1 if act else 0)
         if sole_consumer_is_conv and x.requires_grad:
-            _GN_FWD[out.data_ptr()] = (out, x, sums, gamma, beta, float(eps), 1 if act else 0, groups)
+            _GN_FWD[out.data_ptr()] = (out, x, sums, gamma, beta, float(eps), 1 if act else 0, groups, out._version)
         if split:
             return out, x.view(x.shape)
         return out
@@ -414,7 +415,7 @@ class _GroupNormFn(torch.autograd.Function):
         g, b = gamma.detach(), beta.detach()
         pdt = dtype_code(g)
         fused = _GN_BWD.pop(dout.data_ptr(), None)
-        if fused is not None and fused[0].shape == dout.shape:
+        if fused is not None and fused[0].shape == dout.shape and fused[0]._version == fused[2]:
             # dout is already g = dL/d(pre-activation) and its channel sums were reduced by the conv's dgrad epilogue
             dsdb, act = fused[1], 0
         else:
