@@ -304,3 +304,49 @@ def test_optimizer_step_reaches_the_gemm_operand_packs(vcd, pair, fused):
     with torch.no_grad():
         expect = oracle_forward(ref, x, False)["reconstruction"]
     assert rel_err(after, expect) < 8e-2
+
+
+def test_foreign_hooks_switch_layers_to_unfused_paths_with_the_same_gradients(vcd, pair, monkeypatch):
+    """A forward hook registered by foreign code (sdxl_vae_wrapper.py:91, logit lens during training) moves that layer to
+    the unfused path (separate SiLU, materialised upsample, explicit residual add, stand-alone GroupNorm statistics).
+    Reconstruction and all 248 gradients must agree with the fully fused run on the same inputs and noise."""
+    oracle, model = pair
+    torch.manual_seed(21)
+    x = torch.rand(2, 3, 128, 128, device="cuda") * 2 - 1
+    noise = torch.randn(2, 4, 16, 16, device="cuda")
+    _patch_noise(monkeypatch, noise)
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        dist = model.encode(x).latent_dist
+        rec = model.decode(dist.sample()).sample
+        total, _, _ = vcd.vae_loss({"reconstruction": rec, "latent_dist": dist}, x, 1e-6)
+        total.backward()
+        return rec.detach().clone(), {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
+
+    rec0, g0 = run()
+    names = ["encoder.down_blocks.0.resnets.0.norm1", "encoder.down_blocks.1.resnets.0.conv2",
+             "encoder.down_blocks.0.downsamplers.0.conv", "encoder.mid_block.attentions.0.group_norm",
+             "decoder.up_blocks.1.upsamplers.0.conv", "decoder.up_blocks.2.resnets.0.conv1",
+             "decoder.up_blocks.3.resnets.1.norm2", "decoder.conv_norm_out"]
+    seen = []
+    hooks = [model.get_submodule(n).register_forward_hook(lambda m, i, o, n=n: seen.append((n, tuple(o.shape))))
+             for n in names]
+    try:
+        rec1, g1 = run()
+    finally:
+        for h in hooks:
+            h.remove()
+    assert [n for n, _ in seen] and {n for n, _ in seen} == set(names)
+    assert all(len(s) in (3, 4) for _, s in seen)          # logically [N, C, H, W] (attention GroupNorm: [N, C, T])
+    # different bf16 rounding points (separate SiLU, bf16 upsampled tensor, unsummed weights) through 60 layers: a few
+    # per cent; a wrong hand-off (stale bias-gradient column sums, stale GroupNorm sums) would show as O(1) errors
+    assert rel_err(rec1, rec0) < 5e-2
+    # (to_k.bias has an exactly-zero gradient — softmax is invariant to a per-row constant — so what it holds is rounding
+    # noise: parameters with a negligible gradient norm are not compared)
+    big = max(float(v.norm()) for v in g0.values())
+    errs = {n: rel_err(g1[n], g0[n]) for n in g0 if float(g0[n].norm()) > 1e-4 * big}
+    assert len(errs) > 230
+    worst = max(errs, key=errs.get)
+    med = sorted(errs.values())[len(errs) // 2]
+    assert errs[worst] < 0.2 and med < 3e-2, (worst, errs[worst], med)
