@@ -144,6 +144,8 @@ def test_no_cpu_fallback(vcd):
 def test_bench_flop_model_matches_survey():
     import bench
     assert len(bench.conv_layers(512)) == 64
+    kinds = [l[4] for l in bench.conv_layers(512)]
+    assert kinds.count("up") == 3 and kinds.count("down") == 3 and kinds.count("s1") == 58
     total, conv, attn = bench.train_flops_per_image(512)
     assert abs(conv / 1e9 - 3545.3) < 0.1 and abs(attn / 1e9 - 85.9) < 0.1 and abs(total / 1e12 - 10.89) < 0.01
     total, conv, attn = bench.train_flops_per_image(256)
