@@ -213,6 +213,37 @@ int vcd_dead_weight_count(const void* const* tensors, const int64_t* numels, con
                           double threshold, double mean_percentage, int dead_type, double* sum_abs_ws,
                           int64_t* counts, vcd_stream_t stream);
 
+/* ---- fused multi-tensor gradient norm + clip + AdamW (train.py:184-187,301-302) ----------------
+ * Tables (device arrays of length T): params / grads (fp32 or bf16 per dtypes[t]; grads[t] may be NULL = parameter
+ * skipped this step), exp_avg / exp_avg_sq (fp32), numels.  Work is cut into chunks of vcd_optim_chunk_elems()
+ * elements: chunk c covers elements [chunk_off[c], chunk_off[c] + chunk) of tensor chunk_tensor[c] (device arrays of
+ * length n_chunks, built once by the caller).
+ * vcd_multi_sqnorm    : *out_sqnorm (fp64, zeroed by the call) = sum over all tensors of sum g^2
+ * vcd_clip_adamw_step : g *= min(1, max_norm / (sqrt(*grad_sqnorm) + 1e-6)) (skipped when grad_sqnorm is NULL or
+ *                       max_norm <= 0; torch.nn.utils.clip_grad_norm_), then torch.optim.AdamW's update with decoupled
+ *                       weight decay and bias correction for step number `step` (1-based). */
+int vcd_optim_chunk_elems(void);
+int vcd_multi_sqnorm(const void* const* grads, const int64_t* numels, const int32_t* dtypes,
+                     const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks, double* out_sqnorm,
+                     vcd_stream_t stream);
+int vcd_clip_adamw_step(void* const* params, const void* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, const int64_t* numels, const int32_t* dtypes,
+                        const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks,
+                        const double* grad_sqnorm, double max_norm, double lr, double beta1, double beta2,
+                        double eps, double weight_decay, int64_t step, vcd_stream_t stream);
+
+/* ---- evaluation metrics and input preprocessing (evaluate.py:163-176,238-249; data_utils.py:13-30)
+ * vcd_ssim_psnr_update : pred / target fp32 NCHW in [0, data_range].  ACCUMULATES (caller zeroes once):
+ *                        *ssim_sum += sum over the N images of the per-image mean SSIM ([upstream] torchmetrics
+ *                        StructuralSimilarityIndexMeasure: Gaussian window kernel_size x kernel_size, sigma, valid
+ *                        positions, c1 = (0.01 R)^2, c2 = (0.03 R)^2); *sse += sum (pred - target)^2
+ *                        (PeakSignalNoiseRatio: 10 log10(R^2 / (sse / elements))).
+ * vcd_preprocess_u8    : [N][H][W][3] uint8 -> fp32 [N][3][R][R] in [-1, 1]: Resize(shorter side -> R, bilinear) ->
+ *                        CenterCrop(R) -> ToTensor -> Normalize(0.5, 0.5). */
+int vcd_ssim_psnr_update(const float* pred, const float* target, int N, int C, int H, int W, float data_range,
+                         int kernel_size, float sigma, double* ssim_sum, double* sse, vcd_stream_t stream);
+int vcd_preprocess_u8(const uint8_t* images, float* out, int N, int H, int W, int R, vcd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ def _worker(rank, world, port, q):
         # rank r saw (r + 1) forwards whose per-forward mean|x| vectors sum to base * (r + 1)
         base = torch.tensor([1.0, 2.0, 3.0, 4.0])
         tgt.slot.run.view(5, 4)[0] = base * (rank + 1)
+        tgt.slot.run.view(5, 4)[3] = base * (rank + 1)     # running max|x|: NOT additive across ranks
         tgt.slot.scal[:] = torch.tensor([0.5 * (rank + 1), 0.0, rank + 1.0], dtype=torch.float64)
         mon._targets[tgt.identifier] = tgt
         mon._fired.append(tgt.identifier)
@@ -40,6 +41,8 @@ def _worker(rank, world, port, q):
         ok_stats = bool(abs(data["mean_abs_activation_per_channel"] - want).max() < 1e-6) and \
             abs(float(data["mean_activation"]) - 0.5) < 1e-9 and \
             f"tracking/{tgt.identifier}/mean_abs_activation_per_channel_overall_mean" in wb
+        ext = mon.get_extended_stats_for_step(1)[tgt.identifier]
+        ok_stats = ok_stats and bool(abs(ext["max_abs_per_channel"] - (base * world).numpy()).max() < 1e-6)
         # 2) gamma broadcast: rank 0 "nudges", step() marked the sync, next encode-side hook re-synchronises
         g = vae.decoder.conv_norm_out.weight
         if rank == 0:

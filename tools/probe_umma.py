@@ -8,7 +8,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import vcd_b200
 
-lib = vcd_b200._lib.lib()
+vcd_b200._lib.lib()   # libvcd_b200.so provides make_act_map / error plumbing to the probe library
+_here = os.path.dirname(os.path.abspath(__file__))
+_so = os.path.join(_here, "_probe.so")
+if not os.path.exists(_so):   # the probe kernel is NOT part of the product library: built on demand
+    import subprocess
+    _pkg = os.path.dirname(vcd_b200.LIB_PATH)
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-shared", "-Xcompiler",
+                           "-fPIC", os.path.join(_here, "umma_probe.cu"), "-o", _so, "-L" + _pkg, "-l:libvcd_b200.so",
+                           "-Xlinker", "-rpath=" + _pkg, "-lcuda"])
+lib = C.CDLL(_so)
 fn = lib.vcd_debug_umma_shifted
 fn.restype = C.c_int
 fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

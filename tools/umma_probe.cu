@@ -1,8 +1,8 @@
-// umma_probe.cu — hardware probe (test-only entry point): does a K-major SWIZZLE_128B UMMA A-descriptor work when
+// umma_probe.cu — hardware probe (NOT part of libvcd_b200.so; tools/probe_umma.py builds it into tools/_probe.so): does a K-major SWIZZLE_128B UMMA A-descriptor work when
 // its start address is shifted by whole 128-byte rows inside a TMA-written tile (start not 1024-byte aligned)?
 // This is what lets ONE shared-memory input patch serve all 3x3 taps of an implicit-GEMM convolution.
 //   D[128][N=64] = A[r0 : r0+128][0:64] * B[64][64]^T, A tile = 144 rows x 64 bf16 loaded by one TMA box.
-#include "umma_gemm.cuh"
+#include "../vae-channel-dynamics_b200/csrc/umma_gemm.cuh"
 
 namespace {
 

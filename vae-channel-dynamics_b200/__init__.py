@@ -13,6 +13,8 @@ from ._lib import LIB_PATH, VcdError  # noqa: F401
 from .vae import B200AutoencoderKL, DiagonalGaussianDistribution  # noqa: F401
 from .losses import vae_loss  # noqa: F401
 from .graph_step import GraphedVAEStep  # noqa: F401
+from .optim import FusedClipAdamW  # noqa: F401
+from . import data, metrics  # noqa: F401
 
 SRC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "src")
 

@@ -61,6 +61,11 @@ SIGNATURES = {
     "vcd_classify_mask": (_i, [_p, _f, _p, _p, _i, _p]),
     "vcd_nudge_gamma": (_i, [_p, _i, _i, _p, _i, _d, _d, _i, _p, _p]),
     "vcd_dead_weight_count": (_i, [_p, _p, _p, _i, _d, _d, _i, _p, _p, _p]),
+    "vcd_optim_chunk_elems": (_i, []),
+    "vcd_multi_sqnorm": (_i, [_p, _p, _p, _p, _p, _i, _p, _p]),
+    "vcd_clip_adamw_step": (_i, [_p] * 8 + [_i, _p, _d, _d, _d, _d, _d, _d, _i64, _p]),
+    "vcd_ssim_psnr_update": (_i, [_p, _p, _i, _i, _i, _i, _f, _i, _f, _p, _p, _p]),
+    "vcd_preprocess_u8": (_i, [_p, _p, _i, _i, _i, _i, _p]),
 }
 
 _lib = None

@@ -95,6 +95,72 @@ __device__ __forceinline__ float silu_grad_f(float y) {
   float s = sigmoid_fast(y);
   return s * fmaf(y, 1.f - s, 1.f);
 }
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) -------------------------------------------------------
+// Two fp32 lanes per instruction on the FMA pipe: the streaming kernels (GroupNorm, statistics, optimizer) spend their
+// issue slots on per-element fp32 math, and the packed forms halve that.  A pair lives in a 64-bit register
+// (lo = first element, hi = second).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 dup2(float v) { return pk2(v, v); }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 neg2(f32x2 a) { return a ^ 0x8000000080000000ull; }
+__device__ __forceinline__ f32x2 abs2(f32x2 a) { return a & 0x7fffffff7fffffffull; }
+__device__ __forceinline__ f32x2 max2(f32x2 a, f32x2 b) {
+  float al, ah, bl, bh;
+  upk2(a, al, ah);
+  upk2(b, bl, bh);
+  return pk2(fmaxf(al, bl), fmaxf(ah, bh));
+}
+__device__ __forceinline__ f32x2 tanh2(f32x2 a) {
+  float lo, hi;
+  upk2(a, lo, hi);
+  asm("tanh.approx.f32 %0, %0;" : "+f"(lo));
+  asm("tanh.approx.f32 %0, %0;" : "+f"(hi));
+  return pk2(lo, hi);
+}
+// one 32-bit word holding two bf16 (first element in the low half) <-> an fp32 pair
+__device__ __forceinline__ f32x2 bf2_to_f32x2(uint32_t w) {
+  f32x2 r;
+  uint32_t lo = w << 16, hi = w & 0xffff0000u;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf2(f32x2 v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return f2_to_bf2(lo, hi);
+}
+__device__ __forceinline__ void unpack8x(const bf16x8& p, f32x2* f) {
+  f[0] = bf2_to_f32x2(p.u.x);
+  f[1] = bf2_to_f32x2(p.u.y);
+  f[2] = bf2_to_f32x2(p.u.z);
+  f[3] = bf2_to_f32x2(p.u.w);
+}
+__device__ __forceinline__ bf16x8 pack8x(const f32x2* f) {
+  bf16x8 p;
+  p.u = make_uint4(f32x2_to_bf2(f[0]), f32x2_to_bf2(f[1]), f32x2_to_bf2(f[2]), f32x2_to_bf2(f[3]));
+  return p;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -73,20 +73,71 @@ __device__ __forceinline__ void load_group_stats(const double* sums, int n, int 
 }
 constexpr int kMaxGroups = 64;
 
+// All hot loops below use packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, common.cuh): a thread's 8 channels are 4 pairs.
+// SiLU and its derivative go through ONE tanh per element on the half-argument u = y/2 (constants pre-halved):
+//     silu(y)  = y * sigmoid(y)            = u * (1 + t)                 t = tanh(u)
+//     silu'(y) = s * (1 + y * (1 - s))     = 0.5 * (1 + t + u * (1 - t*t))
+// Latency is hidden by occupancy (3 blocks of 256 threads per SM, 2 pixels = up to 96 bytes in flight per thread), not by
+// register double buffering: the packed math leaves these kernels short of issue pressure, so more resident warps pay.
+
+// five per-channel statistics of one value pair stream: sum, sum of squares, sum |.|, max |.|, #(|.| < tau)
+struct Stat5 {
+  f32x2 s[4], q[4], sa[4], mx[4], nz[4];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0ull;
+  }
+  __device__ __forceinline__ void add(int j, f32x2 y, float tau) {
+    const f32x2 a = abs2(y);
+    s[j] = add2(s[j], y);
+    q[j] = fma2(y, y, q[j]);
+    sa[j] = add2(sa[j], a);
+    mx[j] = max2(mx[j], a);
+    if (tau > 0.f) {   // warp-uniform: the near-zero count costs nothing when no threshold is configured
+      float lo, hi;
+      upk2(a, lo, hi);
+      nz[j] = add2(nz[j], pk2(lo < tau ? 1.f : 0.f, hi < tau ? 1.f : 0.f));
+    }
+  }
+  __device__ __forceinline__ void to_acc(float (*acc)[8]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      upk2(s[j], acc[0][2 * j], acc[0][2 * j + 1]);
+      upk2(q[j], acc[1][2 * j], acc[1][2 * j + 1]);
+      upk2(sa[j], acc[2][2 * j], acc[2][2 * j + 1]);
+      upk2(mx[j], acc[3][2 * j], acc[3][2 * j + 1]);
+      upk2(nz[j], acc[4][2 * j], acc[4][2 * j + 1]);
+    }
+  }
+};
+// block-level reduction of a Stat5 into the [5][C] slot (fp32 atomics: one per channel and statistic per block)
+__device__ __forceinline__ void flush_stat5(const Stat5& st, float* red, const Map& m, float* __restrict__ cstats, int C) {
+  float acc[5][8];
+  st.to_acc(acc);
+  deposit<5>(red, m, acc);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    atomicAdd(&cstats[0 * C + c], lane_sum(red, m, 0, c));
+    atomicAdd(&cstats[1 * C + c], lane_sum(red, m, 1, c));
+    atomicAdd(&cstats[2 * C + c], lane_sum(red, m, 2, c));
+    atomic_max_nonneg(&cstats[3 * C + c], lane_max(red, m, 3, c));
+    const float z = lane_sum(red, m, 4, c);
+    if (z != 0.f) atomicAdd(&cstats[4 * C + c], z);
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------- pass 1: group sums (+ input stats)
 template <bool STATS>
-__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ sums,
-                                                            float* __restrict__ cstats, float near_zero, int HW,
-                                                            int C, int G, int ppb) {
+__global__ void __launch_bounds__(kThreads, 3) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ sums,
+                                                               float* __restrict__ cstats, float near_zero, int HW,
+                                                               int C, int G, int ppb) {
   extern __shared__ float red[];  // [K][8][PL][V] with K = 2 (5 when STATS), then [C][2] channel sums
   constexpr int K = STATS ? 5 : 2;
   const int n = blockIdx.y;
   Map m = make_map(C, HW, ppb);
-  float acc[K][8];
-#pragma unroll
-  for (int k = 0; k < K; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  Stat5 st;
+  st.init();
   const bf16* xb = x + (int64_t)n * HW * C + m.c0;
   for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
     bf16x8 v[kUnroll];
@@ -98,21 +149,21 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restri
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       if (p0 + (int64_t)u * m.PL >= m.p_end) break;
-      float f[8];
-      unpack8(v[u], f);
+      f32x2 f[4];
+      unpack8x(v[u], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += f[j];
-        acc[1][j] += f[j] * f[j];
+      for (int j = 0; j < 4; ++j) {
         if (STATS) {
-          float a = fabsf(f[j]);
-          acc[2][j] += a;
-          acc[3][j] = fmaxf(acc[3][j], a);
-          acc[4][j] += (a < near_zero) ? 1.f : 0.f;
+          st.add(j, f[j], near_zero);
+        } else {
+          st.s[j] = add2(st.s[j], f[j]);
+          st.q[j] = fma2(f[j], f[j], st.q[j]);
         }
       }
     }
   }
+  float acc[5][8];
+  st.to_acc(acc);
   deposit<K>(red, m, acc);
   __syncthreads();
   float* chan = red + K * 8 * kThreads;  // [C][2]
@@ -125,7 +176,8 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restri
       atomicAdd(&cstats[1 * C + c], q);
       atomicAdd(&cstats[2 * C + c], lane_sum(red, m, 2, c));
       atomic_max_nonneg(&cstats[3 * C + c], lane_max(red, m, 3, c));
-      atomicAdd(&cstats[4 * C + c], lane_sum(red, m, 4, c));
+      const float z = lane_sum(red, m, 4, c);
+      if (z != 0.f) atomicAdd(&cstats[4 * C + c], z);
     }
   }
   __syncthreads();
@@ -141,82 +193,93 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const bf16* __restri
   }
 }
 
-// ---------------------------------------------------------------- pass 2: normalise (+ output stats, SiLU)
-template <bool STATS>
-__global__ void __launch_bounds__(kThreads) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ sums,
-                                                            const void* __restrict__ gamma, const void* __restrict__ beta,
-                                                            int pdt, bf16* __restrict__ out, float* __restrict__ cstats,
-                                                            float near_zero, float eps, int act, int HW, int C, int G, int ppb) {
-  extern __shared__ float sm[];  // [5][8][PL][V] when STATS
+// per-thread affine constants of the thread's 8 channels: y = a x + b (ACT: pre-halved, u = y/2 = ka x + kb)
+template <bool ACT>
+__device__ __forceinline__ void load_affine(const void* gamma, const void* beta, int pdt, const float* s_mean,
+                                            const float* s_rstd, int c0, int D, f32x2* ka, f32x2* kb) {
+  const float h = ACT ? 0.5f : 1.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a[2], b[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = c0 + 2 * j + e;
+      a[e] = s_rstd[c / D] * load_param(gamma, pdt, c);
+      b[e] = load_param(beta, pdt, c) - s_mean[c / D] * a[e];
+    }
+    ka[j] = pk2(h * a[0], h * a[1]);
+    kb[j] = pk2(h * b[0], h * b[1]);
+  }
+}
+
+// ---------------------------------------------------------------- pass 2: normalise (+ input / output stats, SiLU)
+// SIN : per-channel statistics of the INPUT x  (capture_point "input" of this GroupNorm == "output" of the layer that
+//       produced x, e.g. encoder.conv_in) — the pass reads x anyway;
+// SOUT: per-channel statistics of y = gamma*xhat + beta BEFORE SiLU (capture_point "output").
+template <bool ACT, bool SIN, bool SOUT>
+__global__ void __launch_bounds__(kThreads, 3) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ sums,
+                                                               const void* __restrict__ gamma, const void* __restrict__ beta,
+                                                               int pdt, bf16* __restrict__ out, float* __restrict__ cstats_in,
+                                                               float* __restrict__ cstats_out, float near_zero, float eps,
+                                                               int HW, int C, int G, int ppb) {
+  extern __shared__ float sm[];  // [5][8][PL][V] when SIN || SOUT
   const int n = blockIdx.y;
   Map m = make_map(C, HW, ppb);
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
   load_group_stats(sums, n, G, cnt, eps, s_mean, s_rstd);
-  float a[8], b[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int c = m.c0 + j;
-    a[j] = s_rstd[c / D] * load_param(gamma, pdt, c);
-    b[j] = load_param(beta, pdt, c) - s_mean[c / D] * a[j];
-  }
-  float s[8], q[8], sa[8], mx[8], nz[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0.f;
+  f32x2 ka[4], kb[4];
+  load_affine<ACT>(gamma, beta, pdt, s_mean, s_rstd, m.c0, D, ka, kb);
+  Stat5 sin, sout;
+  if (SIN) sin.init();
+  if (SOUT) sout.init();
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
-    bf16x8 v[kUnroll];
+  constexpr int U = (SIN && SOUT) ? 2 : kUnroll;
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
+    bf16x8 v[U];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t p = p0 + (int64_t)u * m.PL;
       if (p < m.p_end) v[u] = ld8(x + base + p * C);
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t p = p0 + (int64_t)u * m.PL;
       if (p >= m.p_end) break;
-      float f[8];
-      unpack8(v[u], f);
+      f32x2 f[4];
+      unpack8x(v[u], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float y = fmaf(a[j], f[j], b[j]);
-        if (STATS) {
-          float ab = fabsf(y);
-          s[j] += y;
-          q[j] += y * y;
-          sa[j] += ab;
-          mx[j] = fmaxf(mx[j], ab);
-          nz[j] += (ab < near_zero) ? 1.f : 0.f;
-        }
-        f[j] = act ? silu_f(y) : y;
+      for (int j = 0; j < 4; ++j) {
+        if (SIN) sin.add(j, f[j], near_zero);
+        const f32x2 w = fma2(ka[j], f[j], kb[j]);       // ACT: u = y/2, else y
+        if (SOUT) sout.add(j, ACT ? add2(w, w) : w, near_zero);
+        f[j] = ACT ? fma2(w, tanh2(w), w) : w;           // silu(y) = u + u*tanh(u)
       }
-      st8(out + base + p * C, pack8(f));
+      st8(out + base + p * C, pack8x(f));
     }
   }
-  if (STATS) {
-    float acc[5][8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { acc[0][j] = s[j]; acc[1][j] = q[j]; acc[2][j] = sa[j]; acc[3][j] = mx[j]; acc[4][j] = nz[j]; }
-    deposit<5>(sm, m, acc);
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kThreads) {
-      atomicAdd(&cstats[0 * C + c], lane_sum(sm, m, 0, c));
-      atomicAdd(&cstats[1 * C + c], lane_sum(sm, m, 1, c));
-      atomicAdd(&cstats[2 * C + c], lane_sum(sm, m, 2, c));
-      atomic_max_nonneg(&cstats[3 * C + c], lane_max(sm, m, 3, c));
-      atomicAdd(&cstats[4 * C + c], lane_sum(sm, m, 4, c));
-    }
-  }
+  if (SIN) flush_stat5(sin, sm, m, cstats_in, C);
+  if (SOUT) flush_stat5(sout, sm, m, cstats_out, C);
+}
+
+// g * silu'(y) for one pair: gg = (g/2) * (1 + t + u (1 - t^2)),  u = y/2, t = tanh(u)
+__device__ __forceinline__ f32x2 silu_grad_times(f32x2 g, f32x2 u) {
+  const f32x2 t = tanh2(u);
+  const f32x2 v = fma2(neg2(t), t, dup2(1.f));
+  const f32x2 r = fma2(u, v, t);
+  const f32x2 gh = mul2(g, dup2(0.5f));
+  return fma2(gh, r, gh);
 }
 
 // ---------------------------------------------------------------- backward pass 1: ds/db per (n, c)
-__global__ void __launch_bounds__(kThreads, 2) gn_bwd_reduce_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
-                                                                 const double* __restrict__ sums,
-                                                                 const void* __restrict__ gamma,
-                                                                 const void* __restrict__ beta, int pdt,
-                                                                 float* __restrict__ dsdb, float eps, int act, int HW,
-                                                                 int C, int G, int ppb) {
+template <bool ACT>
+__global__ void __launch_bounds__(kThreads, 3) gn_bwd_reduce_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
+                                                                    const double* __restrict__ sums,
+                                                                    const void* __restrict__ gamma,
+                                                                    const void* __restrict__ beta, int pdt,
+                                                                    float* __restrict__ dsdb, float eps, int HW, int C, int G,
+                                                                    int ppb) {
   extern __shared__ float sm[];  // [2][8][PL][V]
   const int n = blockIdx.y;
   Map m = make_map(C, HW, ppb);
@@ -224,62 +287,42 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_reduce_kernel(const bf16* 
   const double cnt = (double)D * (double)HW;
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
   load_group_stats(sums, n, G, cnt, eps, s_mean, s_rstd);
-  float a[8], b[8], ds[8], db[8];
+  f32x2 ka[4], kb[4], ds[4], db[4];
+  load_affine<ACT>(gamma, beta, pdt, s_mean, s_rstd, m.c0, D, ka, kb);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int c = m.c0 + j;
-    a[j] = s_rstd[c / D] * load_param(gamma, pdt, c);
-    b[j] = load_param(beta, pdt, c) - s_mean[c / D] * a[j];
-    ds[j] = db[j] = 0.f;
-  }
+  for (int j = 0; j < 4; ++j) ds[j] = db[j] = 0ull;
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  // register double buffer: the loads of the next stage are in flight while this stage is reduced
   constexpr int U = 2;
-  const int64_t S = (int64_t)U * m.PL;
-  bf16x8 bx[2][U], bg[2][U];
-  auto load = [&](int64_t q, bf16x8* vx, bf16x8* vg) {
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
+    bf16x8 vx[U], vg[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t pp = q + (int64_t)u * m.PL;
-      if (pp < m.p_end) {
-        vx[u] = ld8(x + base + pp * C);
-        vg[u] = ld8(dout + base + pp * C);
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p < m.p_end) {
+        vx[u] = ld8(x + base + p * C);
+        vg[u] = ld8(dout + base + p * C);
       }
     }
-  };
-  auto compute = [&](int64_t q, const bf16x8* vx, const bf16x8* vg) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (q + (int64_t)u * m.PL >= m.p_end) break;
-      float f[8], g[8];
-      unpack8(vx[u], f);
-      unpack8(vg[u], g);
+      if (p0 + (int64_t)u * m.PL >= m.p_end) break;
+      f32x2 f[4], g[4];
+      unpack8x(vx[u], f);
+      unpack8x(vg[u], g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float gg = g[j];
-        if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
-        ds[j] = fmaf(gg, f[j], ds[j]);
-        db[j] += gg;
+      for (int j = 0; j < 4; ++j) {
+        const f32x2 gg = ACT ? silu_grad_times(g[j], fma2(ka[j], f[j], kb[j])) : g[j];
+        ds[j] = fma2(gg, f[j], ds[j]);
+        db[j] = add2(db[j], gg);
       }
-    }
-  };
-  int64_t pq = m.p_begin + m.pl;
-  if (pq < m.p_end) {
-    load(pq, bx[0], bg[0]);
-    while (true) {
-      if (pq + S < m.p_end) load(pq + S, bx[1], bg[1]);
-      compute(pq, bx[0], bg[0]);
-      pq += S;
-      if (pq >= m.p_end) break;
-      if (pq + S < m.p_end) load(pq + S, bx[0], bg[0]);
-      compute(pq, bx[1], bg[1]);
-      pq += S;
-      if (pq >= m.p_end) break;
     }
   }
   float acc[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { acc[0][j] = ds[j]; acc[1][j] = db[j]; }
+  for (int j = 0; j < 4; ++j) {
+    upk2(ds[j], acc[0][2 * j], acc[0][2 * j + 1]);
+    upk2(db[j], acc[1][2 * j], acc[1][2 * j + 1]);
+  }
   deposit<2>(sm, m, acc);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += kThreads) {
@@ -289,107 +332,103 @@ __global__ void __launch_bounds__(kThreads, 2) gn_bwd_reduce_kernel(const bf16* 
 }
 
 // ---------------------------------------------------------------- backward pass 2: dx
-template <bool HAS_RES>
-__global__ void __launch_bounds__(kThreads, 2) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
-                                                                const double* __restrict__ sums,
-                                                                const void* __restrict__ gamma,
-                                                                const void* __restrict__ beta, int pdt,
-                                                                const float* __restrict__ dsdb, bf16* __restrict__ dx,
-                                                                const bf16* __restrict__ dres,
-                                                                float* __restrict__ colsum, void* __restrict__ dgamma,
-                                                                void* __restrict__ dbeta, int N, float eps, int act,
-                                                                int HW, int C, int G, int ppb) {
+//   dx = a * gg + c2 * x + c3 (+ dres)      gg = dout * silu'(y) (ACT) | dout
+//   ACT: a * gg = (a/2) g (1 + r) = k + k r  with k = ka * g  — the SiLU factor is folded into the final FFMA2
+template <bool ACT, bool HAS_RES>
+__global__ void __launch_bounds__(kThreads, 3) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
+                                                                   const double* __restrict__ sums,
+                                                                   const void* __restrict__ gamma,
+                                                                   const void* __restrict__ beta, int pdt,
+                                                                   const float* __restrict__ dsdb, bf16* __restrict__ dx,
+                                                                   const bf16* __restrict__ dres,
+                                                                   float* __restrict__ colsum, void* __restrict__ dgamma,
+                                                                   void* __restrict__ dbeta, int N, float eps,
+                                                                   int HW, int C, int G, int ppb) {
   extern __shared__ float sm[];  // [1][8][PL][V] when colsum
-  constexpr int kU = 2;          // fewer pixels in flight than the other passes: three streams per pixel
   const int n = blockIdx.y;
   Map m = make_map(C, HW, ppb);
-  float cs[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
   const int D = C / G;
   const double cnt = (double)D * (double)HW;
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
   load_group_stats(sums, n, G, cnt, eps, s_mean, s_rstd);
-  float a[8], b[8], c2[8], c3[8];
-  int prev_g = -1;
-  float pc2 = 0.f, pc3 = 0.f;
+  f32x2 ka[4], kb[4], c2[4], c3[4], cs[4];
+  load_affine<ACT>(gamma, beta, pdt, s_mean, s_rstd, m.c0, D, ka, kb);
+  {
+    int prev_g = -1;
+    float pc2 = 0.f, pc3 = 0.f, t2[8], t3[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int c = m.c0 + j;
-    int g = c / D;
-    const float mean = s_mean[g], rstd = s_rstd[g];
-    a[j] = rstd * load_param(gamma, pdt, c);
-    b[j] = load_param(beta, pdt, c) - mean * a[j];
-    if (g != prev_g) {
-      float S1 = 0.f, S2 = 0.f;
-      for (int k = 0; k < D; ++k) {
-        int cc = g * D + k;
-        float gm = load_param(gamma, pdt, cc);
-        S1 += gm * dsdb[((int64_t)n * C + cc) * 2];
-        S2 += gm * dsdb[((int64_t)n * C + cc) * 2 + 1];
+    for (int j = 0; j < 8; ++j) {
+      const int c = m.c0 + j, g = c / D;
+      if (g != prev_g) {
+        const float mean = s_mean[g], rstd = s_rstd[g];
+        float S1 = 0.f, S2 = 0.f;
+        for (int k = 0; k < D; ++k) {
+          const int cc = g * D + k;
+          const float gm = load_param(gamma, pdt, cc);
+          S1 += gm * dsdb[((int64_t)n * C + cc) * 2];
+          S2 += gm * dsdb[((int64_t)n * C + cc) * 2 + 1];
+        }
+        const float inv = 1.f / (float)cnt;
+        pc2 = (S2 * mean - S1) * rstd * rstd * rstd * inv;
+        pc3 = -pc2 * mean - S2 * rstd * inv;
+        prev_g = g;
       }
-      float inv = 1.f / (float)cnt;
-      pc2 = (S2 * mean - S1) * rstd * rstd * rstd * inv;
-      pc3 = -pc2 * mean - S2 * rstd * inv;
-      prev_g = g;
+      t2[j] = pc2;
+      t3[j] = pc3;
     }
-    c2[j] = pc2;
-    c3[j] = pc3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      c2[j] = pk2(t2[2 * j], t2[2 * j + 1]);
+      c3[j] = pk2(t3[2 * j], t3[2 * j + 1]);
+      cs[j] = 0ull;
+    }
   }
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  // register double buffer: the loads of the next stage are in flight while this stage is computed and stored
-  const int64_t S = (int64_t)kU * m.PL;
-  bf16x8 bx[2][kU], bg[2][kU], br[2][kU];
-  auto load = [&](int64_t q, bf16x8* vx, bf16x8* vg, bf16x8* vr) {
+  constexpr int U = 2;
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
+    bf16x8 vx[U], vg[U], vr[U];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int64_t pp = q + (int64_t)u * m.PL;
-      if (pp < m.p_end) {
-        vx[u] = ld8(x + base + pp * C);
-        vg[u] = ld8(dout + base + pp * C);
-        if (HAS_RES) vr[u] = ld8(dres + base + pp * C);
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p < m.p_end) {
+        vx[u] = ld8(x + base + p * C);
+        vg[u] = ld8(dout + base + p * C);
+        if (HAS_RES) vr[u] = ld8(dres + base + p * C);
       }
     }
-  };
-  auto compute = [&](int64_t q, const bf16x8* vx, const bf16x8* vg, const bf16x8* vr) {
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int64_t pp = q + (int64_t)u * m.PL;
-      if (pp >= m.p_end) break;
-      float f[8], g[8], r[8];
-      unpack8(vx[u], f);
-      unpack8(vg[u], g);
-      if (HAS_RES) unpack8(vr[u], r);
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + (int64_t)u * m.PL;
+      if (p >= m.p_end) break;
+      f32x2 f[4], g[4], r[4];
+      unpack8x(vx[u], f);
+      unpack8x(vg[u], g);
+      if (HAS_RES) unpack8x(vr[u], r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float gg = g[j];
-        if (act) gg *= silu_grad_f(fmaf(a[j], f[j], b[j]));
-        float d = fmaf(a[j], gg, fmaf(c2[j], f[j], c3[j]));
-        if (HAS_RES) d += r[j];
+      for (int j = 0; j < 4; ++j) {
+        f32x2 e = fma2(c2[j], f[j], c3[j]);
+        if (HAS_RES) e = add2(e, r[j]);
+        f32x2 d;
+        if (ACT) {
+          const f32x2 uu = fma2(ka[j], f[j], kb[j]);
+          const f32x2 t = tanh2(uu);
+          const f32x2 v = fma2(neg2(t), t, dup2(1.f));
+          const f32x2 rr = fma2(uu, v, t);
+          const f32x2 k = mul2(ka[j], g[j]);
+          d = fma2(k, rr, add2(e, k));
+        } else {
+          d = fma2(ka[j], g[j], e);
+        }
+        cs[j] = add2(cs[j], d);
         g[j] = d;
-        cs[j] += d;
       }
-      st8(dx + base + pp * C, pack8(g));
-    }
-  };
-  int64_t pq = m.p_begin + m.pl;
-  if (pq < m.p_end) {
-    load(pq, bx[0], bg[0], br[0]);
-    while (true) {
-      if (pq + S < m.p_end) load(pq + S, bx[1], bg[1], br[1]);
-      compute(pq, bx[0], bg[0], br[0]);
-      pq += S;
-      if (pq >= m.p_end) break;
-      if (pq + S < m.p_end) load(pq + S, bx[0], bg[0], br[0]);
-      compute(pq, bx[1], bg[1], br[1]);
-      pq += S;
-      if (pq >= m.p_end) break;
+      st8(dx + base + p * C, pack8x(g));
     }
   }
   if (colsum) {
     float acc[1][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[0][j] = cs[j];
+    for (int j = 0; j < 4; ++j) upk2(cs[j], acc[0][2 * j], acc[0][2 * j + 1]);
     deposit<1>(sm, m, acc);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kThreads) atomicAdd(&colsum[c], lane_sum(sm, m, 0, c));
@@ -490,33 +529,11 @@ GnShape gn_launch_shape(int N, int HW, int C, int bps) {
 
 }  // namespace
 
-// The GEMM kernels around these kernels run with the maximum shared-memory carveout (~206 KB dynamic shared memory);
-// asking for the same carveout here avoids an SM-wide L1/shared-memory reconfiguration at every kernel boundary
-// (these kernels stream and do not rely on L1).  VCD_CARVEOUT=0 disables it (A/B measurement).
-static void prefer_max_shared_once() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  // measured on B200 (bench.py, 20 steps, A/B twice): 92.4 ms/step with the preference, 91.1 ms without — the streaming
-  // kernels do profit from L1, so the preference is opt-in only
-  const char* e = getenv("VCD_CARVEOUT");
-  if (!(e && e[0] == '1')) return;
-  const int c = cudaSharedmemCarveoutMaxShared;
-  cudaFuncSetAttribute(gn_ab_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(gn_apply_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(gn_bwd_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(gn_bwd_apply_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(gn_bwd_apply_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-  cudaFuncSetAttribute(gn_param_grad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-}
-
+// (measured in round 1: asking for the GEMM kernels' maximum shared-memory carveout here made the step 1.4 % slower —
+// the streaming kernels do profit from L1 — so no carveout preference is set)
 int gn_make_ab(const double* sums, const void* gamma, const void* beta, int pdt, float eps, int N, int HW, int C, int G,
                float* ab, cudaStream_t st) {
   if (check_shape(C, G)) return -1;
-  prefer_max_shared_once();
   gn_ab_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, gamma, beta, pdt, eps, N, HW, C, G, ab);
   VCD_LAUNCH_CHECK();
   return 0;
@@ -525,7 +542,6 @@ int gn_make_ab(const double* sums, const void* gamma, const void* beta, int pdt,
 extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, float near_zero, int N, int HW, int C,
                             int G, vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
-  prefer_max_shared_once();
   cudaStream_t st = as_stream(stream);
   VCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * G, st));
   const GnShape sh = gn_launch_shape(N, HW, C, 4);
@@ -540,18 +556,29 @@ extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, f
 }
 
 extern "C" int vcd_gn_apply_fwd(const void* x, const double* sums, const void* gamma, const void* beta, int param_dtype,
-                                void* out, float* chan_stats_out, float near_zero, float eps, int act_silu, int N,
-                                int HW, int C, int G, vcd_stream_t stream) {
+                                void* out, float* chan_stats_in, float* chan_stats_out, float near_zero, float eps,
+                                int act_silu, int N, int HW, int C, int G, vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
-  prefer_max_shared_once();
   cudaStream_t st = as_stream(stream);
   const GnShape sh = gn_launch_shape(N, HW, C, 3);
-  if (chan_stats_out)
-    gn_apply_kernel<true><<<sh.grid, kThreads, 5 * 8 * kThreads * sizeof(float), st>>>(
-        (const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, chan_stats_out, near_zero, eps, act_silu, HW, C, G, sh.ppb);
-  else
-    gn_apply_kernel<false><<<sh.grid, kThreads, 0, st>>>((const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, nullptr,
-                                                         near_zero, eps, act_silu, HW, C, G, sh.ppb);
+  const bool sin = chan_stats_in != nullptr, sout = chan_stats_out != nullptr;
+  const size_t smem = (sin || sout) ? 5 * 8 * kThreads * sizeof(float) : 0;
+#define VCD_GN_APPLY(ACT, SIN, SOUT)                                                                                   \
+  gn_apply_kernel<ACT, SIN, SOUT><<<sh.grid, kThreads, smem, st>>>((const bf16*)x, sums, gamma, beta, param_dtype,     \
+                                                                   (bf16*)out, chan_stats_in, chan_stats_out, near_zero, \
+                                                                   eps, HW, C, G, sh.ppb)
+  const int sel = (act_silu ? 4 : 0) | (sin ? 2 : 0) | (sout ? 1 : 0);
+  switch (sel) {
+    case 0: VCD_GN_APPLY(false, false, false); break;
+    case 1: VCD_GN_APPLY(false, false, true); break;
+    case 2: VCD_GN_APPLY(false, true, false); break;
+    case 3: VCD_GN_APPLY(false, true, true); break;
+    case 4: VCD_GN_APPLY(true, false, false); break;
+    case 5: VCD_GN_APPLY(true, false, true); break;
+    case 6: VCD_GN_APPLY(true, true, false); break;
+    default: VCD_GN_APPLY(true, true, true); break;
+  }
+#undef VCD_GN_APPLY
   VCD_LAUNCH_CHECK();
   return 0;
 }
@@ -560,12 +587,16 @@ extern "C" int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* 
                                  int param_dtype, float* dsdb, float eps, int act_silu, int N, int HW, int C, int G,
                                  vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
-  prefer_max_shared_once();
   cudaStream_t st = as_stream(stream);
   VCD_CUDA(cudaMemsetAsync(dsdb, 0, sizeof(float) * 2 * N * C, st));
-  const GnShape sh = gn_launch_shape(N, HW, C, 2);
-  gn_bwd_reduce_kernel<<<sh.grid, kThreads, 2 * 8 * kThreads * sizeof(float), st>>>(
-      (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, eps, act_silu, HW, C, G, sh.ppb);
+  const GnShape sh = gn_launch_shape(N, HW, C, 3);
+  const size_t smem = 2 * 8 * kThreads * sizeof(float);
+  if (act_silu)
+    gn_bwd_reduce_kernel<true><<<sh.grid, kThreads, smem, st>>>((const bf16*)x, (const bf16*)dout, sums, gamma, beta,
+                                                                param_dtype, dsdb, eps, HW, C, G, sh.ppb);
+  else
+    gn_bwd_reduce_kernel<false><<<sh.grid, kThreads, smem, st>>>((const bf16*)x, (const bf16*)dout, sums, gamma, beta,
+                                                                 param_dtype, dsdb, eps, HW, C, G, sh.ppb);
   VCD_LAUNCH_CHECK();
   return 0;
 }
@@ -575,18 +606,20 @@ extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* s
                                 void* dgamma, void* dbeta, float eps, int act_silu, int N, int HW, int C, int G,
                                 vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
-  prefer_max_shared_once();
-  if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, as_stream(stream)));
+  cudaStream_t st = as_stream(stream);
+  if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
   const size_t smem = dx_colsum ? 8 * kThreads * sizeof(float) : 0;
-  const GnShape sh = gn_launch_shape(N, HW, C, 2);
-  if (dres)
-    gn_bwd_apply_kernel<true><<<sh.grid, kThreads, smem, as_stream(stream)>>>(
-        (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum,
-        dgamma, dbeta, N, eps, act_silu, HW, C, G, sh.ppb);
-  else
-    gn_bwd_apply_kernel<false><<<sh.grid, kThreads, smem, as_stream(stream)>>>(
-        (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, nullptr, dx_colsum, dgamma, dbeta,
-        N, eps, act_silu, HW, C, G, sh.ppb);
+  const GnShape sh = gn_launch_shape(N, HW, C, 3);
+#define VCD_GN_BWD(ACT, RES)                                                                                              \
+  gn_bwd_apply_kernel<ACT, RES><<<sh.grid, kThreads, smem, st>>>((const bf16*)x, (const bf16*)dout, sums, gamma, beta,    \
+                                                                 param_dtype, dsdb, (bf16*)dx, (const bf16*)dres,         \
+                                                                 dx_colsum, dgamma, dbeta, N, eps, HW, C, G, sh.ppb)
+  if (act_silu) {
+    if (dres) VCD_GN_BWD(true, true); else VCD_GN_BWD(true, false);
+  } else {
+    if (dres) VCD_GN_BWD(false, true); else VCD_GN_BWD(false, false);
+  }
+#undef VCD_GN_BWD
   VCD_LAUNCH_CHECK();
   return 0;
 }
@@ -594,7 +627,6 @@ extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* s
 extern "C" int vcd_gn_param_grad(const double* sums, const float* dsdb, void* dgamma, void* dbeta, int param_dtype,
                                  float eps, int N, int HW, int C, int G, vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
-  prefer_max_shared_once();
   gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(sums, dsdb, dgamma, dbeta, param_dtype, eps, N, HW,
                                                                        C, G);
   VCD_LAUNCH_CHECK();

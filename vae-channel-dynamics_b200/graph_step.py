@@ -31,14 +31,34 @@ class GraphedVAEStep:
         dev = self.params[0].device
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=dt, device=dev)
+        self._views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self._attach_grads()
         self.static_x = example.detach().clone()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._out = None
         self._capture(warmup)
+
+    def _attach_grads(self):
+        """`p.grad` of every parameter IS its view of the flat buffer the captured backward accumulates into.
+        The reference loop calls optimizer.zero_grad(set_to_none=True) every step (train.py:304), which drops these
+        aliases; they are restored before every replay (the buffer itself is zeroed inside the graph)."""
+        for p, v in zip(self.params, self._views):
+            g = p.grad
+            if g is None or g.data_ptr() != v.data_ptr():
+                p.grad = v
+
+    def _slots(self):
+        seen = []
+        for m in self.wrapper.modules():
+            for a in ("_track_in", "_track_out"):
+                s = getattr(m, a, None)
+                if s is not None and all(s is not t for t in seen):
+                    seen.append(s)
+        return seen
 
     def _fwd_bwd(self):
         self.flat.zero_()
@@ -48,6 +68,9 @@ class GraphedVAEStep:
         return total.detach(), rec.detach(), kl.detach()
 
     def _capture(self, warmup: int):
+        # the warm-up and capture forwards run on an example batch: the statistics slots of a subscribed
+        # ActivityMonitor must not count them (snapshot here, restore after the capture)
+        saved = [(s, s.raw.clone(), s.run.clone(), s.scal.clone()) for s in self._slots()]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -60,6 +83,10 @@ class GraphedVAEStep:
         with torch.cuda.graph(self.graph):
             self._out = self._fwd_bwd()
         self.launches_per_replay = _lib.launches - l0   # C-ABI compute calls recorded in the graph
+        for s, raw, run, scal in saved:
+            s.raw.copy_(raw)
+            s.run.copy_(run)
+            s.scal.copy_(scal)
 
     def refresh(self):
         """Re-capture (e.g. after hooks were added/removed, which changes the kernel sequence)."""
@@ -69,6 +96,7 @@ class GraphedVAEStep:
         vae = getattr(self.wrapper, "vae", None)
         if vae is not None and hasattr(vae, "_sync_gamma_if_pending"):
             vae._sync_gamma_if_pending()        # eager: Python-side flag, not part of the graph
+        self._attach_grads()
         self.static_x.copy_(pixel_values, non_blocking=True)
         self.graph.replay()
         if self.world > 1:

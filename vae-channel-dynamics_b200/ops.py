@@ -383,7 +383,9 @@ class _GroupNormFn(torch.autograd.Function):
         x = _nhwc(x)
         N, C = x.shape[0], x.shape[-1]
         hw = x.numel() // (N * C)
-        sums = pop_gn_sums(x, groups) if slot_in is None else None
+        sums = pop_gn_sums(x, groups)   # always popped: an entry left behind would pin x until the next encode()
+        if slot_in is not None:
+            sums = None                 # input statistics are tracked: the statistics pass runs anyway and fills the slot
         if sums is None:   # not produced by the epilogue of the GEMM that wrote x (or input statistics are tracked)
             sums = torch.empty(N * groups * 2, dtype=torch.float64, device=x.device)
             call("vcd_gn_stats", _p(x), _p(sums), _p(None if slot_in is None else slot_in.raw),

@@ -53,15 +53,24 @@ class InterventionHandler:
             raise _lib.VcdError("InterventionHandler: parameters must be on a CUDA device (no CPU path)")
         if not data.is_contiguous():
             raise _lib.VcdError("InterventionHandler: GroupNorm scale must be contiguous")
-        idx = torch.tensor([int(i) for i in indices], dtype=torch.int64, device=data.device)
-        applied = torch.empty(1, dtype=torch.int32, device=data.device)
+        # the reference walks the list sequentially (nudger.py:128-143), so a repeated index is nudged (and rounded to
+        # the parameter dtype, and counted) once per occurrence: pass k holds the indices that occur more than k times —
+        # no two threads of one launch touch the same element
+        ints = [int(i) for i in indices]
+        mult: Dict[int, int] = {}
+        for i in ints:
+            mult[i] = mult.get(i, 0) + 1
+        n = 0
+        applied = torch.zeros(1, dtype=torch.int32, device=data.device)
         with torch.cuda.device(data.device):
-            _lib.call("vcd_nudge_gamma", data.data_ptr(), ops.dtype_code(data), data.numel(), idx.data_ptr(),
-                      idx.numel(), self.nudge_factor, self.max_scale_value, mode, applied.data_ptr(),
-                      torch.cuda.current_stream().cuda_stream)
-        n = int(applied.item())
-        for i in indices:
-            if not (0 <= int(i) < data.numel()):
+            for k in range(max(mult.values())):
+                idx = torch.tensor([i for i, m in mult.items() if m > k], dtype=torch.int64, device=data.device)
+                _lib.call("vcd_nudge_gamma", data.data_ptr(), ops.dtype_code(data), data.numel(), idx.data_ptr(),
+                          idx.numel(), self.nudge_factor, self.max_scale_value, mode, applied.data_ptr(),
+                          torch.cuda.current_stream().cuda_stream)
+                n += int(applied.item())
+        for i in ints:
+            if not (0 <= i < data.numel()):
                 logger.warning(f"Inactive index {i} out of bounds (size: {data.numel()})")
         return n
 

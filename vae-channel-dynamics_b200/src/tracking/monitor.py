@@ -205,11 +205,24 @@ class ActivityMonitor:
         if not tgts:
             return {}
         dev = tgts[0].slot.run.device
-        flat = torch.cat([t.slot.run.double() for t in tgts] + [t.slot.scal for t in tgts])
+        if any(t.slot.run.device != dev for t in tgts):   # model split over devices: pack on the first slot's device
+            runs = [t.slot.run.to(dev) for t in tgts]
+            scals = [t.slot.scal.to(dev) for t in tgts]
+        else:
+            runs, scals = [t.slot.run for t in tgts], [t.slot.scal for t in tgts]
+        flat = torch.cat([r.double() for r in runs] + scals)
         if torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
-            # sum of per-forward means over all ranks; max rows are summed too and not reported multi-rank
+            # sums of per-forward means over all ranks in ONE packed SUM all-reduce; the running max|x| rows (row 3 of
+            # every slot) are not additive: they travel in a second, tiny MAX all-reduce
+            mx = torch.cat([r.view(5, -1)[3] for r in runs]).double()
             torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+            torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+            off = 0
+            for r in runs:
+                c = r.numel() // 5
+                flat[off + 3 * c: off + 4 * c] = mx[off // 5: off // 5 + c]
+                off += 5 * c
         host = flat.cpu().numpy()
         out, off = {}, 0
         for t in tgts:

@@ -143,7 +143,9 @@ class ResnetBlock2D(nn.Module):
         h = self.conv1(h)
         h = _norm_act(self.norm2, h, conv=self.conv2)
         sc = x if self.conv_shortcut is None else self.conv_shortcut(x)
-        if _hooked(self.conv2):
+        if _hooked(self.conv2) or self.conv2._track_out is not None:
+            # a hook / statistics slot on conv2 must observe the PRE-residual tensor (the reference adds the skip
+            # connection outside the module): explicit add instead of the residual epilogue
             return _logi(ops.add(_phys(self.conv2(h)), _phys(sc)))
         return self.conv2(h, residual=sc)
 
@@ -168,7 +170,10 @@ class Attention(nn.Module):
             h, tokens = (_phys(t) for t in self.group_norm(_logi(tokens), split=True))
         q, k, v = self.to_q(h), self.to_k(h), self.to_v(h)
         o = ops.attention_core(q, k, v)
-        o = self.to_out[0](o, residual=tokens)
+        if _hooked(self.to_out[0]):   # the hook sees the projection alone; the residual is added outside the module
+            o = ops.add(self.to_out[0](o), tokens)
+        else:
+            o = self.to_out[0](o, residual=tokens)
         return _logi(o.reshape(N, H, W, C))
 
 
@@ -404,6 +409,8 @@ class B200AutoencoderKL(nn.Module):
         return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True):
+        if not torch.is_grad_enabled():
+            ops.clear_colsums()     # decode-only loops (wrapper.decode, logit lens): drop stale producer->consumer hand-offs
         y = self.decoder(self.post_quant_conv(z))          # logical [N, 3, H, W] bf16
         sample = ops.to_nchw(_phys(y), self.output_dtype)  # contiguous NCHW, fp32
         sample._vcd_nhwc = _phys(y)                        # fused-loss fast path (vcd_b200.losses)
