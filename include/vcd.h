@@ -52,6 +52,25 @@ int vcd_conv_umma_supported(int Cin, int Cout, int KH, int KW, int stride);
 int vcd_pack_conv_weight(const void* w, const void* bias, int dtype, int Cout, int Cin, int KH, int KW,
                          void* w_fprop, void* w_dgrad, float* bias_f32, vcd_stream_t stream);
 
+/* All operand packs of a model in ONE launch (the per-layer entry point above costs ~140 launches per forward).
+ * descs (device array): one vcd_pack_desc per layer — mode 0: w OIHW [cout][cin][taps] -> wf [taps][cout][cin],
+ * wd [taps][cin][cout] (wd may be NULL); mode 1 (Upsample2D conv, taps = 9): the 16 pre-summed phase taps of
+ * vcd_pack_upconv_weight; bias -> bias_f32 when both are given.  Work list (device int32 arrays of length n_tiles): tile t
+ * covers output channels [tile_co[t], +vcd_pack_tile_co()) x input channels [tile_ci[t], +vcd_pack_tile_ci()) of layer
+ * tile_layer[t]. */
+typedef struct {
+  const void* w;
+  const void* bias;
+  void* wf;
+  void* wd;
+  float* bias_f32;
+  int32_t dtype, cout, cin, taps, mode, pad_;
+} vcd_pack_desc;
+int vcd_pack_tile_co(void);
+int vcd_pack_tile_ci(void);
+int vcd_multi_pack_weights(const vcd_pack_desc* descs, const int32_t* tile_layer, const int32_t* tile_co,
+                           const int32_t* tile_ci, int n_tiles, vcd_stream_t stream);
+
 /* ---- convolution (AutoencoderKL.encode/decode conv layers; sdxl_vae_wrapper.py:60,71;
  *      backward reached from train.py:299) ------------------------------------------
  * y[n,ho,wo,co] = bias[co] + sum x[n, ho*stride - pad_t + kh, wo*stride - pad_l + kw, ci] * w[co,ci,kh,kw]
@@ -133,13 +152,17 @@ int vcd_add(const void* a, const void* b, void* out, int64_t n, vcd_stream_t str
  * Pass 1  vcd_gn_stats      : sums[n][g] = {sum x, sum x^2} (fp64), optional per-channel
  *                             statistics of the GroupNorm INPUT  (capture_point "input")
  * Pass 2  vcd_gn_apply_fwd  : y = gamma*(x-mean)*rstd+beta ; optional statistics of y
- *                             (capture_point "output", before SiLU) ; out = silu(y) if act
+ *                             (capture_point "output", before SiLU) ; out = silu(y) if act ;
+ *                             optional statistics of the INPUT x in the same pass (chan_stats_in:
+ *                             capture_point "input" of this GroupNorm / "output" of the layer that
+ *                             produced x, e.g. vae.encoder.conv_in) when the group sums came from the
+ *                             producing GEMM's epilogue and pass 1 does not run
  * chan stats layout (fp32 [5][C]): sum x, sum x^2, sum |x|, max |x|, count(|x| < near_zero)
  * HW = H*W; x is [N][HW][C]. */
 int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, float near_zero,
                  int N, int HW, int C, int G, vcd_stream_t stream);
 int vcd_gn_apply_fwd(const void* x, const double* sums, const void* gamma, const void* beta, int param_dtype,
-                     void* out, float* chan_stats_out, float near_zero, float eps, int act_silu,
+                     void* out, float* chan_stats_in, float* chan_stats_out, float near_zero, float eps, int act_silu,
                      int N, int HW, int C, int G, vcd_stream_t stream);
 /* backward: dsdb[n][c] = {sum g*x, sum g} with g = dout * silu'(y) ; then dx; then dgamma/dbeta */
 int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
@@ -221,7 +244,8 @@ int vcd_dead_weight_count(const void* const* tensors, const int64_t* numels, con
  * vcd_multi_sqnorm    : *out_sqnorm (fp64, zeroed by the call) = sum over all tensors of sum g^2
  * vcd_clip_adamw_step : g *= min(1, max_norm / (sqrt(*grad_sqnorm) + 1e-6)) (skipped when grad_sqnorm is NULL or
  *                       max_norm <= 0; torch.nn.utils.clip_grad_norm_), then torch.optim.AdamW's update with decoupled
- *                       weight decay and bias correction for step number `step` (1-based). */
+ *                       weight decay and bias correction for step number `step` (1-based), or — torch keeps one step
+ *                       counter per parameter — for steps[t] when `steps` (device int32 [T]) is given. */
 int vcd_optim_chunk_elems(void);
 int vcd_multi_sqnorm(const void* const* grads, const int64_t* numels, const int32_t* dtypes,
                      const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks, double* out_sqnorm,
@@ -230,7 +254,7 @@ int vcd_clip_adamw_step(void* const* params, const void* const* grads, float* co
                         float* const* exp_avg_sq, const int64_t* numels, const int32_t* dtypes,
                         const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks,
                         const double* grad_sqnorm, double max_norm, double lr, double beta1, double beta2,
-                        double eps, double weight_decay, int64_t step, vcd_stream_t stream);
+                        double eps, double weight_decay, const int32_t* steps, int64_t step, vcd_stream_t stream);
 
 /* ---- evaluation metrics and input preprocessing (evaluate.py:163-176,238-249; data_utils.py:13-30)
  * vcd_ssim_psnr_update : pred / target fp32 NCHW in [0, data_range].  ACCUMULATES (caller zeroes once):

@@ -7,7 +7,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from util import rel_err
+from util import record_parity, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -75,13 +75,17 @@ def test_forward_backward_matches_oracle(vcd, pair, monkeypatch, impl, R, B):
         mt, mrec, mkl = vcd.vae_loss({"reconstruction": rec, "latent_dist": dist}, x, 1e-6)
         mt.backward()
 
+        measured = {}
+
         def gate(ours, truth, ref16, ceiling, what):
             e_ours, e_ref = rel_err(ours, truth), rel_err(ref16, truth)
+            measured[what] = {"e_ours": e_ours, "e_ref16": e_ref}
             assert e_ours < 1.5 * e_ref + 5e-3, (what, e_ours, e_ref)
             assert e_ours < ceiling, (what, e_ours)
 
-        gate(dist.mean, oo["latent_dist"].mean, r16_mean, 5e-2, "latent mean")
-        gate(rec, oo["reconstruction"], r16_rec, 8e-2, "reconstruction")
+        # fixed ceilings = 1.25x the errors measured on B200 at the worst of the three cases (profiles/r02_parity.json)
+        gate(dist.mean, oo["latent_dist"].mean, r16_mean, 2.75e-2, "latent mean")
+        gate(rec, oo["reconstruction"], r16_rec, 4.0e-2, "reconstruction")
         assert abs(float(mrec) - float(orec)) < 1e-2 * float(orec)
         assert abs(float(mkl) - float(okl)) < 1e-2 * float(okl)
         # train.py's own torch mse on the fp32 reconstruction gives the same number as the fused kernel
@@ -91,9 +95,11 @@ def test_forward_backward_matches_oracle(vcd, pair, monkeypatch, impl, R, B):
         e_ours = torch.tensor([rel_err(p.grad, og[n].grad) for n, p in model.named_parameters()])
         e_ref = torch.tensor([rel_err(r16_g[n], og[n].grad) for n, _ in model.named_parameters()])
         assert all(p.grad is not None and p.grad.dtype == p.dtype for p in model.parameters())
+        measured["grad_median"] = {"e_ours": float(e_ours.median()), "e_ref16": float(e_ref.median())}
+        record_parity(f"test_model_gpu three_way impl={impl} R={R} B={B} params=fp32", measured)
         assert float(e_ours.median()) < 1.5 * float(e_ref.median()) + 5e-3, (float(e_ours.median()), float(e_ref.median()))
         assert float(e_ours.max()) < 1.5 * float(e_ref.max()) + 2e-2, (float(e_ours.max()), float(e_ref.max()))
-        assert float(e_ours.median()) < 5e-2
+        assert float(e_ours.median()) < 3.4e-2
         if impl == "auto" and R >= 256:
             assert vcd._lib.lib().vcd_pair_kernel_launches() - n_pair0 >= 150
     finally:
@@ -350,3 +356,28 @@ def test_foreign_hooks_switch_layers_to_unfused_paths_with_the_same_gradients(vc
     worst = max(errs, key=errs.get)
     med = sorted(errs.values())[len(errs) // 2]
     assert errs[worst] < 0.2 and med < 3e-2, (worst, errs[worst], med)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_model_wide_weight_pack_equals_per_layer_packs(vcd, dtype):
+    """vcd_multi_pack_weights (one launch for all layers of the encoder / decoder) writes exactly the operand packs the
+    per-layer entry points vcd_pack_conv_weight / vcd_pack_upconv_weight write — including the 3-, 4- and 8-channel layers
+    whose tiles are ragged — and the packs are only trusted inside the encode()/decode() call they were built for."""
+    ops = vcd.ops
+    vae = vcd.B200AutoencoderKL.from_pretrained("random-init:5", torch_dtype=dtype).cuda()
+    n = 0
+    for which in ("encoder", "decoder"):
+        l0 = vcd._lib.launches
+        plan = vae._pack_weights(which)
+        assert vcd._lib.launches - l0 == 1
+        for w, b, packs, mode in plan.layers:
+            assert packs.valid
+            ref = ops.UpconvPackedWeights() if mode == 1 else ops.PackedWeights()
+            wf, wd, bias = ref.get(w, b)
+            assert torch.equal(wf, packs.wf) and torch.equal(wd, packs.wd), (which, tuple(w.shape), mode)
+            assert (bias is None) == (packs.bias is None) and (bias is None or torch.equal(bias, packs.bias))
+            n += 1
+        plan.expire()
+        assert not any(p.valid for _, _, p, _ in plan.layers)
+    assert n == 64 + 8           # 64 convs + 8 attention projections
+    assert sum(1 for which in ("encoder", "decoder") for _, _, _, m in vae._pack_weights(which).layers if m == 1) == 3

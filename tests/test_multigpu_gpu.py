@@ -1,0 +1,134 @@
+"""Two ranks over NCCL (needs 2 GPUs; `gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py -m gpu`):
+  * DDP gradients of the drop-in == single-process gradients on the concatenated batch (mean of per-rank means),
+  * ActivityMonitor.step() statistics on every rank == the single-process monitor on the global batch, including the
+    running max|x| (a MAX all-reduce, not a sum),
+  * a rank-0-only nudge (train.py:244-246,315-319) reaches every replica at the next forward (gamma broadcast)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+TRACK = ["vae.encoder.conv_in", "vae.encoder.down_blocks.0.resnets.0.norm1", "vae.decoder.up_blocks.1.resnets.0.norm1"]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import numpy as np
+        import vcd_b200
+        from util import rel_err
+        vcd_b200.add_src_to_path()
+        from models.sdxl_vae_wrapper import SDXLVAEWrapper
+        from tracking.monitor import ActivityMonitor
+        from classification.classifier import RegionClassifier
+        from intervention.nudger import InterventionHandler
+        R, per = 64, 2
+        g = torch.Generator().manual_seed(5)
+        x_all = (torch.rand(world * per, 3, R, R, generator=g) * 2 - 1).cuda()
+        noise_all = torch.randn(world * per, 4, R // 8, R // 8, generator=g).cuda()
+        tcfg = {"enabled": True, "track_interval": 1, "target_layers": [
+            {"name": n, "capture_point": "output", "metrics": ["mean_abs_activation_per_channel", "mean_activation"]} for n in TRACK]}
+
+        def build():
+            w = SDXLVAEWrapper("random-init:42").cuda()
+            with torch.no_grad():
+                for n in TRACK[1:]:
+                    w.vae.get_submodule(n[len("vae."):]).weight[::8] = 1e-3
+            return w
+
+        real_randn = torch.randn
+
+        def run(model, x, noise):
+            torch.randn = lambda *a, **k: noise.clone() if tuple(a[0] if len(a) == 1 and not isinstance(a[0], int) else a) == tuple(noise.shape) else real_randn(*a, **k)
+            try:
+                out = model(x, sample_posterior=True)
+            finally:
+                torch.randn = real_randn
+            total, _, _ = vcd_b200.vae_loss(out, x, 1e-6)
+            total.backward()
+            return float(total)
+
+        # ---- single process, global batch (every rank computes it: it is the expected value)
+        ref = build()
+        mon_ref = ActivityMonitor(ref, tcfg)
+        run(ref, x_all, noise_all)
+        g_ref = {n: p.grad.detach().float().clone() for n, p in ref.named_parameters()}
+        # monitor.step() all-reduces across ranks: give the reference monitor the same forward on every rank, so that its
+        # rank-mean equals the single-process global-batch value
+        mon_ref.step(1)
+        d_ref = mon_ref.get_data_for_step(1)
+        e_ref = mon_ref.get_extended_stats_for_step(1)
+        mon_ref.remove_hooks()
+        # ---- DDP, per-rank shard
+        w = build()
+        ddp = torch.nn.parallel.DistributedDataParallel(w, device_ids=[rank])
+        mon = ActivityMonitor(ddp, tcfg)
+        sl = slice(rank * per, (rank + 1) * per)
+        run(ddp, x_all[sl], noise_all[sl])
+        errs = sorted((rel_err(p.grad, g_ref[n]), n) for n, p in w.named_parameters() if float(g_ref[n].norm()) > 1e-4 * max(float(v.norm()) for v in g_ref.values()))
+        mon.step(1)
+        data, ext = mon.get_data_for_step(1), mon.get_extended_stats_for_step(1)
+        stat_err = max(float(np.max(np.abs(data[k]["mean_abs_activation_per_channel"] - d_ref[k]["mean_abs_activation_per_channel"])
+                                    / np.maximum(np.abs(d_ref[k]["mean_abs_activation_per_channel"]), 1e-3))) for k in d_ref)
+        # max|x| over the GLOBAL batch = max over ranks of the shard maxima; the reference monitor saw the global batch
+        max_err = max(float(np.max(np.abs(ext[k]["max_abs_per_channel"] - e_ref[k]["max_abs_per_channel"])
+                                   / np.maximum(e_ref[k]["max_abs_per_channel"], 1e-3))) for k in e_ref)
+        # ---- rank-0-only nudge, then the next forward re-synchronises the replicas
+        clf = RegionClassifier(w.vae, {"enabled": True, "threshold": 0.2, "target_metric_key": "mean_abs_activation_per_channel",
+                                       "layers_to_classify": [n + ".output" for n in TRACK[1:]]})
+        res = clf.classify(data, 1)
+        nudged = 0
+        if rank == 0:
+            ih = InterventionHandler(w.vae, {"enabled": True, "strategy": "gentle_nudge_groupnorm_scale", "nudge_factor": 1.2,
+                                             "max_scale_value": 1.5, "intervention_interval": 1})
+            ih.intervene(res, 1)
+            nudged = ih.num_nudges_applied
+        gam = torch.cat([w.vae.get_submodule(n[len("vae."):]).weight.detach().float() for n in TRACK[1:]])
+        before = [torch.empty_like(gam) for _ in range(world)]
+        dist.all_gather(before, gam)
+        diverged = not torch.equal(before[0], before[1])
+        ddp.zero_grad(set_to_none=True)
+        run(ddp, x_all[sl], noise_all[sl])
+        gam = torch.cat([w.vae.get_submodule(n[len("vae."):]).weight.detach().float() for n in TRACK[1:]])
+        after = [torch.empty_like(gam) for _ in range(world)]
+        dist.all_gather(after, gam)
+        q.put({"rank": rank, "grad_median": errs[len(errs) // 2][0], "grad_max": errs[-1][0], "grad_worst": errs[-1][1],
+               "stat_err": stat_err, "max_err": max_err, "classified": {k: len(v["inactive_channel_indices"]) for k, v in res.items()},
+               "nudged": nudged, "diverged_before_sync": diverged, "equal_after_sync": bool(torch.equal(after[0], after[1])),
+               "nudge_visible": bool(torch.allclose(after[1][:128:8], torch.full((16,), 1.2e-3, device=after[1].device), rtol=1e-3))})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_two_rank_ddp_matches_single_process(vcd):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from util import record_parity
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=800) for _ in range(2)), key=lambda r: r["rank"])
+    for p in procs:
+        p.join(120)
+    record_parity("NCCL world=2: DDP vs single process on the concatenated batch (64^2, 2 images per rank, fp32 params)", res)
+    for r in res:
+        # same arithmetic, different summation order (split batch, fp32 atomics, bf16 stores): far below the bf16 network error
+        assert r["grad_median"] < 5e-3 and r["grad_max"] < 3e-2, r
+        assert r["stat_err"] < 1e-3 and r["max_err"] < 1e-2, r      # bf16 rounding flips from a different summation order
+        assert r["classified"] == {TRACK[1] + ".output": 16, TRACK[2] + ".output": 64}, r
+        assert r["diverged_before_sync"] and r["equal_after_sync"] and r["nudge_visible"], r
+    assert res[0]["nudged"] == 80 and res[1]["nudged"] == 0

@@ -101,7 +101,7 @@ def _compare_runs(ours, ref, tag, stat_tol, weight_tol):
     return res
 
 
-def _run_both(vcd, tmp_path, base_yaml, overrides, tag, stat_tol, eval_tol, weight_tol, env_b200=None):
+def _run_both(vcd, tmp_path, base_yaml, overrides, tag, stat_tol, eval_tol, weight_tol, env_b200=None, evaluate=True):
     if rh.reference_dir() is None:
         pytest.skip("baseline/_ref is missing: run __graft_entry__.build() where /root/reference exists")
     wd = str(tmp_path)
@@ -118,6 +118,8 @@ def _run_both(vcd, tmp_path, base_yaml, overrides, tag, stat_tol, eval_tol, weig
         run_name = yaml.safe_load(open(cfg))["run_name"]
         runs[arm] = (cfg, os.path.join(ov["output_dir"], run_name), log)
     res = _compare_runs(runs["b200"][1], runs["oracle"][1], tag, stat_tol, weight_tol)
+    if not evaluate:
+        return res
     # ---- evaluate.py on each run's own final_model (from_pretrained of what save_pretrained wrote)
     ev = {}
     for arm in ("b200", "oracle"):
@@ -155,5 +157,7 @@ def test_unchanged_train_py_bf16_nudge_config_with_fused_optimizer(vcd, tmp_path
         "data": {"max_samples": 128, "validation_max_samples": 16, "batch_size": 16, "validation_batch_size": 16, "num_workers": 0},
         "training": {"num_train_epochs": 5, "mixed_precision": "bf16"},
     }, "train.py unchanged: experiment_cifar10_nudge.yaml bf16 40 steps (fused clip+AdamW)", stat_tol=4e-2, eval_tol=5e-2,
-        weight_tol=5e-3, env_b200={"VCD_FUSED_OPT": "1"})
+        weight_tol=5e-3, env_b200={"VCD_FUSED_OPT": "1"},
+        # the reference's evaluate.py cannot run a bf16 config in EITHER arm: evaluate.py:97 does getattr(torch, "bf16")
+        evaluate=False)
     assert [r.split(",")[0] for r in res["intervention_history"]] == ["20", "40"]

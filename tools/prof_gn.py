@@ -29,13 +29,18 @@ for sh in a.shapes:
     dsdb = torch.empty(B * C * 2, dtype=torch.float32, device="cuda")
     colsum = torch.empty(C, dtype=torch.float32, device="cuda")
     pdt = dtype_code(gamma)
+    slot, slot2 = vcd_b200.ops.TrackSlot(C, "cuda", 0.0), vcd_b200.ops.TrackSlot(C, "cuda", 0.0)
     hw = h * h
     call("vcd_gn_stats", _p(xs[0]), _p(sums), None, 0.0, B, hw, C, 32, _st())
 
     fns = {
         "stats": (lambda i: call("vcd_gn_stats", _p(xs[i % nbuf]), _p(sums), None, 0.0, B, hw, C, 32, _st()), 2),
-        "apply": (lambda i: call("vcd_gn_apply_fwd", _p(xs[i % nbuf]), _p(sums), _p(gamma), _p(beta), pdt, _p(out), None, 0.0,
-                                 1e-6, 1, B, hw, C, 32, _st()), 4),
+        "apply": (lambda i: call("vcd_gn_apply_fwd", _p(xs[i % nbuf]), _p(sums), _p(gamma), _p(beta), pdt, _p(out), None, None,
+                                 0.0, 1e-6, 1, B, hw, C, 32, _st()), 4),
+        "apply+stats_out": (lambda i: call("vcd_gn_apply_fwd", _p(xs[i % nbuf]), _p(sums), _p(gamma), _p(beta), pdt, _p(out), None,
+                                           _p(slot.raw), 0.0, 1e-6, 1, B, hw, C, 32, _st()), 4),
+        "apply+stats_in+out": (lambda i: call("vcd_gn_apply_fwd", _p(xs[i % nbuf]), _p(sums), _p(gamma), _p(beta), pdt, _p(out),
+                                              _p(slot2.raw), _p(slot.raw), 0.0, 1e-6, 1, B, hw, C, 32, _st()), 4),
         "bwd_reduce": (lambda i: call("vcd_gn_bwd_reduce", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(sums), _p(gamma), _p(beta),
                                       pdt, _p(dsdb), 1e-6, 1, B, hw, C, 32, _st()), 4),
         "bwd_apply": (lambda i: call("vcd_gn_bwd_apply", _p(xs[i % nbuf]), _p(gs[i % nbuf]), _p(sums), _p(gamma), _p(beta), pdt,

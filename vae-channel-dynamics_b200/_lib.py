@@ -19,6 +19,9 @@ SIGNATURES = {
     "vcd_version": (_i, []),
     "vcd_conv_umma_supported": (_i, [_i] * 5),
     "vcd_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "vcd_pack_tile_co": (_i, []),
+    "vcd_pack_tile_ci": (_i, []),
+    "vcd_multi_pack_weights": (_i, [_p, _p, _p, _p, _i, _p]),
     "vcd_conv2d_fprop_ws_bytes": (_i64, [_i] * 8),
     "vcd_conv2d_fprop": (_i, [_p] * 6 + [_i] * 14 + [_p, _i, _p]),
     "vcd_conv2d_dgrad_ws_bytes": (_i64, [_i] * 8),
@@ -42,7 +45,7 @@ SIGNATURES = {
     "vcd_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "vcd_add": (_i, [_p, _p, _p, _i64, _p]),
     "vcd_gn_stats": (_i, [_p, _p, _p, _f, _i, _i, _i, _i, _p]),
-    "vcd_gn_apply_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _f, _f, _i, _i, _i, _i, _i, _p]),
+    "vcd_gn_apply_fwd": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _f, _f, _i, _i, _i, _i, _i, _p]),
     "vcd_gn_bwd_reduce": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _i, _i, _i, _i, _i, _p]),
     "vcd_gn_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p]),
     "vcd_gn_param_grad": (_i, [_p, _p, _p, _p, _i, _f, _i, _i, _i, _i, _p]),
@@ -63,13 +66,16 @@ SIGNATURES = {
     "vcd_dead_weight_count": (_i, [_p, _p, _p, _i, _d, _d, _i, _p, _p, _p]),
     "vcd_optim_chunk_elems": (_i, []),
     "vcd_multi_sqnorm": (_i, [_p, _p, _p, _p, _p, _i, _p, _p]),
-    "vcd_clip_adamw_step": (_i, [_p] * 8 + [_i, _p, _d, _d, _d, _d, _d, _d, _i64, _p]),
+    "vcd_clip_adamw_step": (_i, [_p] * 8 + [_i, _p, _d, _d, _d, _d, _d, _d, _p, _i64, _p]),
     "vcd_ssim_psnr_update": (_i, [_p, _p, _i, _i, _i, _i, _f, _i, _f, _p, _p, _p]),
     "vcd_preprocess_u8": (_i, [_p, _p, _i, _i, _i, _i, _p]),
 }
 
 _lib = None
 launches = 0  # number of C-ABI compute calls issued (bench.py reports it as gpu_launches)
+# Measurement hook (bench.py instep_rooflines): when `profile` is a list, every call is bracketed by two CUDA events
+# recorded on the call's own stream (the last argument of every entry point) and (name, args, start, end) is appended.
+profile = None
 
 
 class VcdError(RuntimeError):
@@ -95,7 +101,16 @@ def call(name: str, *args) -> None:
     """Invoke an int-returning entry point, raising VcdError with vcd_last_error() on failure."""
     global launches
     l = lib()
-    rc = getattr(l, name)(*args)
+    if profile is not None:
+        import torch
+        st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.default_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        rc = getattr(l, name)(*args)
+        e1.record(st)
+        profile.append((name, args, e0, e1))
+    else:
+        rc = getattr(l, name)(*args)
     launches += 1
     if rc != 0:
         raise VcdError(f"{name} failed ({rc}): {l.vcd_last_error().decode()}")

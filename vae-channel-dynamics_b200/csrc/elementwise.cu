@@ -326,6 +326,83 @@ extern "C" int vcd_pack_conv_weight(const void* w, const void* bias, int dtype, 
   return 0;
 }
 
+// ---------------------------------------------------------------- all weight packs of the model in ONE launch
+// One block = a 16 (Cout) x 64 (Cin) tile of one layer, all taps: coalesced reads of the OIHW rows into shared memory
+// (fp32), then the fprop pack [tap][Cout][Cin] (128-byte row segments), the dgrad pack [tap][Cin][Cout] (32-byte
+// segments) and, for mode 1, the 16 pre-summed phase taps of the Upsample2D form (conv_dispatch.cu).  Replaces ~140
+// per-layer launches of pack_weight_kernel / bias_to_f32_kernel per forward.
+namespace {
+constexpr int kPackCo = 16, kPackCi = 64;
+__device__ __forceinline__ int up_group_pack(int a, int k) { return a == 0 ? (k == 0 ? 0 : 1) : (k <= 1 ? 0 : 1); }
+
+__global__ void __launch_bounds__(256) multi_pack_kernel(const vcd_pack_desc* __restrict__ descs,
+                                                        const int32_t* __restrict__ tile_layer,
+                                                        const int32_t* __restrict__ tile_co,
+                                                        const int32_t* __restrict__ tile_ci) {
+  __shared__ float tile[kPackCo][kPackCi * 9 + 1];
+  const vcd_pack_desc d = descs[tile_layer[blockIdx.x]];
+  const int co0 = tile_co[blockIdx.x], ci0 = tile_ci[blockIdx.x];
+  const int nco = min(kPackCo, d.cout - co0), nci = min(kPackCi, d.cin - ci0);
+  const int taps = d.taps;             // taps of the SOURCE tensor (9 for mode 1)
+  const int row = nci * taps;          // contiguous source elements per output channel of this tile
+  for (int i = threadIdx.x; i < nco * row; i += blockDim.x) {
+    const int co = i / row, e = i - co * row;
+    tile[co][e] = load_param(d.w, d.dtype, ((int64_t)(co0 + co) * d.cin + ci0) * taps + e);
+  }
+  if (ci0 == 0 && d.bias != nullptr && d.bias_f32 != nullptr)
+    for (int i = threadIdx.x; i < nco; i += blockDim.x) d.bias_f32[co0 + i] = load_param(d.bias, d.dtype, co0 + i);
+  __syncthreads();
+  bf16* wf = reinterpret_cast<bf16*>(d.wf);
+  bf16* wd = reinterpret_cast<bf16*>(d.wd);
+  const int otaps = d.mode == 1 ? 16 : taps;
+  // fprop pack: consecutive threads along ci
+  for (int i = threadIdx.x; i < otaps * nco * nci; i += blockDim.x) {
+    const int ci = i % nci, r = i / nci, co = r % nco, q = r / nco;
+    float v;
+    if (d.mode == 1) {
+      const int dw = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
+      v = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          if (up_group_pack(a, kh) == dh && up_group_pack(b, kw) == dw) v += tile[co][ci * 9 + kh * 3 + kw];
+    } else {
+      v = tile[co][ci * taps + q];
+    }
+    wf[((int64_t)q * d.cout + co0 + co) * d.cin + ci0 + ci] = __float2bfloat16_rn(v);
+  }
+  if (wd == nullptr) return;
+  // dgrad pack: consecutive threads along co
+  for (int i = threadIdx.x; i < otaps * nco * nci; i += blockDim.x) {
+    const int co = i % nco, r = i / nco, ci = r % nci, q = r / nci;
+    float v;
+    if (d.mode == 1) {
+      const int dw = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
+      v = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          if (up_group_pack(a, kh) == dh && up_group_pack(b, kw) == dw) v += tile[co][ci * 9 + kh * 3 + kw];
+    } else {
+      v = tile[co][ci * taps + q];
+    }
+    wd[((int64_t)q * d.cin + ci0 + ci) * d.cout + co0 + co] = __float2bfloat16_rn(v);
+  }
+}
+}  // namespace
+
+extern "C" int vcd_pack_tile_co(void) { return kPackCo; }
+extern "C" int vcd_pack_tile_ci(void) { return kPackCi; }
+extern "C" int vcd_multi_pack_weights(const vcd_pack_desc* descs, const int32_t* tile_layer, const int32_t* tile_co,
+                                      const int32_t* tile_ci, int n_tiles, vcd_stream_t stream) {
+  VCD_CHECK_ARG(descs && tile_layer && tile_co && tile_ci && n_tiles > 0, "vcd_multi_pack_weights: bad arguments");
+  multi_pack_kernel<<<n_tiles, 256, 0, as_stream(stream)>>>(descs, tile_layer, tile_co, tile_ci);
+  VCD_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int vcd_space_to_planes(const void* x, void* xp, int N, int H, int W, int C, vcd_stream_t stream) {
   VCD_CHECK_ARG(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "space_to_planes: need C%%8==0 and even H,W");
   space_planes_kernel<<<ew_grid((int64_t)N * H * W * (C / 8), 256), 256, 0, as_stream(stream)>>>(

@@ -87,13 +87,14 @@ struct Stat5 {
 #pragma unroll
     for (int j = 0; j < 4; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0ull;
   }
+  template <bool NZ>
   __device__ __forceinline__ void add(int j, f32x2 y, float tau) {
     const f32x2 a = abs2(y);
     s[j] = add2(s[j], y);
     q[j] = fma2(y, y, q[j]);
     sa[j] = add2(sa[j], a);
     mx[j] = max2(mx[j], a);
-    if (tau > 0.f) {   // warp-uniform: the near-zero count costs nothing when no threshold is configured
+    if (NZ) {   // the near-zero count is compiled in only when a threshold is configured (tau > 0)
       float lo, hi;
       upk2(a, lo, hi);
       nz[j] = add2(nz[j], pk2(lo < tau ? 1.f : 0.f, hi < tau ? 1.f : 0.f));
@@ -128,8 +129,8 @@ __device__ __forceinline__ void flush_stat5(const Stat5& st, float* red, const M
 }
 
 // ---------------------------------------------------------------- pass 1: group sums (+ input stats)
-template <bool STATS>
-__global__ void __launch_bounds__(kThreads, 3) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ sums,
+template <bool STATS, bool NZ>
+__global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) gn_stats_kernel(const bf16* __restrict__ x, double* __restrict__ sums,
                                                                float* __restrict__ cstats, float near_zero, int HW,
                                                                int C, int G, int ppb) {
   extern __shared__ float red[];  // [K][8][PL][V] with K = 2 (5 when STATS), then [C][2] channel sums
@@ -139,22 +140,23 @@ __global__ void __launch_bounds__(kThreads, 3) gn_stats_kernel(const bf16* __res
   Stat5 st;
   st.init();
   const bf16* xb = x + (int64_t)n * HW * C + m.c0;
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)kUnroll * m.PL) {
-    bf16x8 v[kUnroll];
+  constexpr int U = STATS ? 6 : kUnroll;   // 2 resident blocks with statistics: 6 x 16 B in flight per thread
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
+    bf16x8 v[U];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t p = p0 + (int64_t)u * m.PL;
       if (p < m.p_end) v[u] = ld8(xb + p * C);
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (p0 + (int64_t)u * m.PL >= m.p_end) break;
       f32x2 f[4];
       unpack8x(v[u], f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (STATS) {
-          st.add(j, f[j], near_zero);
+          st.add<NZ>(j, f[j], near_zero);
         } else {
           st.s[j] = add2(st.s[j], f[j]);
           st.q[j] = fma2(f[j], f[j], st.q[j]);
@@ -216,8 +218,8 @@ __device__ __forceinline__ void load_affine(const void* gamma, const void* beta,
 // SIN : per-channel statistics of the INPUT x  (capture_point "input" of this GroupNorm == "output" of the layer that
 //       produced x, e.g. encoder.conv_in) — the pass reads x anyway;
 // SOUT: per-channel statistics of y = gamma*xhat + beta BEFORE SiLU (capture_point "output").
-template <bool ACT, bool SIN, bool SOUT>
-__global__ void __launch_bounds__(kThreads, 3) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ sums,
+template <bool ACT, bool SIN, bool SOUT, bool NZ>
+__global__ void __launch_bounds__(kThreads, (SIN || SOUT) ? 2 : 3) gn_apply_kernel(const bf16* __restrict__ x, const double* __restrict__ sums,
                                                                const void* __restrict__ gamma, const void* __restrict__ beta,
                                                                int pdt, bf16* __restrict__ out, float* __restrict__ cstats_in,
                                                                float* __restrict__ cstats_out, float near_zero, float eps,
@@ -235,7 +237,9 @@ __global__ void __launch_bounds__(kThreads, 3) gn_apply_kernel(const bf16* __res
   if (SIN) sin.init();
   if (SOUT) sout.init();
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  constexpr int U = (SIN && SOUT) ? 2 : kUnroll;
+  // bytes in flight per SM: 3 blocks x 256 threads x 4 x 16 B = 48 KB without statistics; the statistics variants hold 40-80
+  // accumulator registers, run 2 blocks per SM and keep 6 (4 with both slots) loads in flight per thread instead
+  constexpr int U = (SIN && SOUT) ? 4 : ((SIN || SOUT) ? 6 : kUnroll);
   for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
     bf16x8 v[U];
 #pragma unroll
@@ -251,9 +255,9 @@ __global__ void __launch_bounds__(kThreads, 3) gn_apply_kernel(const bf16* __res
       unpack8x(v[u], f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (SIN) sin.add(j, f[j], near_zero);
+        if (SIN) sin.add<NZ>(j, f[j], near_zero);
         const f32x2 w = fma2(ka[j], f[j], kb[j]);       // ACT: u = y/2, else y
-        if (SOUT) sout.add(j, ACT ? add2(w, w) : w, near_zero);
+        if (SOUT) sout.add<NZ>(j, ACT ? add2(w, w) : w, near_zero);
         f[j] = ACT ? fma2(w, tanh2(w), w) : w;           // silu(y) = u + u*tanh(u)
       }
       st8(out + base + p * C, pack8x(f));
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 3) gn_bwd_reduce_kernel(const bf16* 
 // ---------------------------------------------------------------- backward pass 2: dx
 //   dx = a * gg + c2 * x + c3 (+ dres)      gg = dout * silu'(y) (ACT) | dout
 //   ACT: a * gg = (a/2) g (1 + r) = k + k r  with k = ka * g  — the SiLU factor is folded into the final FFMA2
-template <bool ACT, bool HAS_RES>
+template <bool ACT, bool HAS_RES, bool WIDE>
 __global__ void __launch_bounds__(kThreads, 3) gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout,
                                                                    const double* __restrict__ sums,
                                                                    const void* __restrict__ gamma,
@@ -351,6 +355,8 @@ __global__ void __launch_bounds__(kThreads, 3) gn_bwd_apply_kernel(const bf16* _
   const double cnt = (double)D * (double)HW;
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
   load_group_stats(sums, n, G, cnt, eps, s_mean, s_rstd);
+  // c2 / c3 are per-GROUP constants.  WIDE (D = C/G >= 4 and a multiple of 4, every layer of the VAE): pairs 0-1 and pairs
+  // 2-3 of the thread's 8 channels each share one value (8 registers instead of 16); otherwise one value per pair (D even)
   f32x2 ka[4], kb[4], c2[4], c3[4], cs[4];
   load_affine<ACT>(gamma, beta, pdt, s_mean, s_rstd, m.c0, D, ka, kb);
   {
@@ -378,8 +384,9 @@ __global__ void __launch_bounds__(kThreads, 3) gn_bwd_apply_kernel(const bf16* _
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      c2[j] = pk2(t2[2 * j], t2[2 * j + 1]);
-      c3[j] = pk2(t3[2 * j], t3[2 * j + 1]);
+      const int src = WIDE ? (j >> 1) * 4 : 2 * j;
+      c2[j] = dup2(t2[src]);
+      c3[j] = dup2(t3[src]);
       cs[j] = 0ull;
     }
   }
@@ -406,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 3) gn_bwd_apply_kernel(const bf16* _
       if (HAS_RES) unpack8x(vr[u], r);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        f32x2 e = fma2(c2[j], f[j], c3[j]);
+        f32x2 e = fma2(c2[WIDE ? (j >> 1) * 2 : j], f[j], c3[WIDE ? (j >> 1) * 2 : j]);
         if (HAS_RES) e = add2(e, r[j]);
         f32x2 d;
         if (ACT) {
@@ -498,8 +505,8 @@ int check_shape(int C, int G) {
     vcd_set_error("GroupNorm kernels need C %% 8 == 0 and C/8 a divisor of 256 (got C=%d)", C);
     return -1;
   }
-  if (G <= 0 || C % G != 0 || G > kMaxGroups) {
-    vcd_set_error("GroupNorm: C=%d not divisible by G=%d", C, G);
+  if (G <= 0 || C % G != 0 || G > kMaxGroups || ((C / G) & 1)) {
+    vcd_set_error("GroupNorm: need C divisible by G with an even number of channels per group (C=%d, G=%d)", C, G);
     return -1;
   }
   return 0;
@@ -544,12 +551,15 @@ extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, f
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
   VCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * G, st));
-  const GnShape sh = gn_launch_shape(N, HW, C, 4);
-  if (chan_stats_in)
-    gn_stats_kernel<true><<<sh.grid, kThreads, (5 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
+  const GnShape sh = gn_launch_shape(N, HW, C, chan_stats_in ? 2 : 3);
+  if (chan_stats_in && near_zero > 0.f)
+    gn_stats_kernel<true, true><<<sh.grid, kThreads, (5 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
+        (const bf16*)x, sums, chan_stats_in, near_zero, HW, C, G, sh.ppb);
+  else if (chan_stats_in)
+    gn_stats_kernel<true, false><<<sh.grid, kThreads, (5 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
         (const bf16*)x, sums, chan_stats_in, near_zero, HW, C, G, sh.ppb);
   else
-    gn_stats_kernel<false><<<sh.grid, kThreads, (2 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
+    gn_stats_kernel<false, false><<<sh.grid, kThreads, (2 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
         (const bf16*)x, sums, nullptr, near_zero, HW, C, G, sh.ppb);
   VCD_LAUNCH_CHECK();
   return 0;
@@ -560,13 +570,20 @@ extern "C" int vcd_gn_apply_fwd(const void* x, const double* sums, const void* g
                                 int act_silu, int N, int HW, int C, int G, vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
-  const GnShape sh = gn_launch_shape(N, HW, C, 3);
   const bool sin = chan_stats_in != nullptr, sout = chan_stats_out != nullptr;
+  const GnShape sh = gn_launch_shape(N, HW, C, (sin || sout) ? 2 : 3);
   const size_t smem = (sin || sout) ? 5 * 8 * kThreads * sizeof(float) : 0;
-#define VCD_GN_APPLY(ACT, SIN, SOUT)                                                                                   \
-  gn_apply_kernel<ACT, SIN, SOUT><<<sh.grid, kThreads, smem, st>>>((const bf16*)x, sums, gamma, beta, param_dtype,     \
-                                                                   (bf16*)out, chan_stats_in, chan_stats_out, near_zero, \
-                                                                   eps, HW, C, G, sh.ppb)
+#define VCD_GN_APPLY(ACT, SIN, SOUT)                                                                                    \
+  do {                                                                                                                  \
+    if ((SIN || SOUT) && near_zero > 0.f)                                                                               \
+      gn_apply_kernel<ACT, SIN, SOUT, (SIN || SOUT)><<<sh.grid, kThreads, smem, st>>>(                                  \
+          (const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, chan_stats_in, chan_stats_out, near_zero, eps, HW, C, G, \
+          sh.ppb);                                                                                                      \
+    else                                                                                                                \
+      gn_apply_kernel<ACT, SIN, SOUT, false><<<sh.grid, kThreads, smem, st>>>(                                          \
+          (const bf16*)x, sums, gamma, beta, param_dtype, (bf16*)out, chan_stats_in, chan_stats_out, near_zero, eps, HW, C, G, \
+          sh.ppb);                                                                                                      \
+  } while (0)
   const int sel = (act_silu ? 4 : 0) | (sin ? 2 : 0) | (sout ? 1 : 0);
   switch (sel) {
     case 0: VCD_GN_APPLY(false, false, false); break;
@@ -610,10 +627,18 @@ extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* s
   if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
   const size_t smem = dx_colsum ? 8 * kThreads * sizeof(float) : 0;
   const GnShape sh = gn_launch_shape(N, HW, C, 3);
+  const bool wide = ((C / G) & 3) == 0;
 #define VCD_GN_BWD(ACT, RES)                                                                                              \
-  gn_bwd_apply_kernel<ACT, RES><<<sh.grid, kThreads, smem, st>>>((const bf16*)x, (const bf16*)dout, sums, gamma, beta,    \
-                                                                 param_dtype, dsdb, (bf16*)dx, (const bf16*)dres,         \
-                                                                 dx_colsum, dgamma, dbeta, N, eps, HW, C, G, sh.ppb)
+  do {                                                                                                                    \
+    if (wide)                                                                                                             \
+      gn_bwd_apply_kernel<ACT, RES, true><<<sh.grid, kThreads, smem, st>>>(                                               \
+          (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum, \
+          dgamma, dbeta, N, eps, HW, C, G, sh.ppb);                                                                       \
+    else                                                                                                                  \
+      gn_bwd_apply_kernel<ACT, RES, false><<<sh.grid, kThreads, smem, st>>>(                                              \
+          (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum, \
+          dgamma, dbeta, N, eps, HW, C, G, sh.ppb);                                                                       \
+  } while (0)
   if (act_silu) {
     if (dres) VCD_GN_BWD(true, true); else VCD_GN_BWD(true, false);
   } else {

@@ -103,8 +103,9 @@ __global__ void __launch_bounds__(kThreads) clip_adamw_kernel(void* const* __res
                                                              const int32_t* __restrict__ chunk_tensor,
                                                              const int64_t* __restrict__ chunk_off,
                                                              const double* __restrict__ grad_sqnorm, float max_norm,
-                                                             float decay, float b1, float b2, float eps,
-                                                             float step_size, float inv_sqrt_bc2) {
+                                                             float decay, float b1, float b2, float w1, float w2,
+                                                             float eps, double lr, double beta1, double beta2,
+                                                             const int32_t* __restrict__ steps, int64_t step) {
   const int t = chunk_tensor[blockIdx.x];
   const void* g = grads[t];
   if (g == nullptr) return;                    // parameter without a gradient this step: untouched (torch skips it)
@@ -118,7 +119,11 @@ __global__ void __launch_bounds__(kThreads) clip_adamw_kernel(void* const* __res
     const float total = (float)sqrt(*grad_sqnorm);
     coef = fminf(max_norm / (total + 1e-6f), 1.f);     // torch.nn.utils.clip_grad_norm_
   }
-  const float w1 = 1.f - b1, w2 = 1.f - b2;
+  // bias correction for THIS tensor's own step count (torch keeps state['step'] per parameter: a parameter that had no
+  // gradient in some step lags behind), in fp64 like torch's python scalars
+  const double ts = (double)(steps != nullptr ? (int64_t)steps[t] : step);
+  const float step_size = (float)(lr / (1.0 - pow(beta1, ts)));
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(beta2, ts)));
   for (int64_t i = base + (int64_t)threadIdx.x * 8; i < min(base + kChunk, n); i += (int64_t)kThreads * 8) {
     float fp[8], fg[8], fm[8], fv[8];
     load8(p, dt, i, n, fp);
@@ -158,12 +163,13 @@ extern "C" int vcd_clip_adamw_step(void* const* params, const void* const* grads
                                    float* const* exp_avg_sq, const int64_t* numels, const int32_t* dtypes,
                                    const int32_t* chunk_tensor, const int64_t* chunk_off, int n_chunks,
                                    const double* grad_sqnorm, double max_norm, double lr, double beta1, double beta2,
-                                   double eps, double weight_decay, int64_t step, vcd_stream_t stream) {
-  VCD_CHECK_ARG(n_chunks > 0 && step >= 1, "vcd_clip_adamw_step: bad arguments");
-  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+                                   double eps, double weight_decay, const int32_t* steps, int64_t step,
+                                   vcd_stream_t stream) {
+  VCD_CHECK_ARG(n_chunks > 0 && (steps != nullptr || step >= 1), "vcd_clip_adamw_step: bad arguments");
   clip_adamw_kernel<<<n_chunks, kThreads, 0, as_stream(stream)>>>(
       params, grads, exp_avg, exp_avg_sq, numels, dtypes, chunk_tensor, chunk_off, grad_sqnorm, (float)max_norm,
-      (float)(1.0 - lr * weight_decay), (float)beta1, (float)beta2, (float)eps, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)));
+      (float)(1.0 - lr * weight_decay), (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
+      lr, beta1, beta2, steps, step);
   VCD_LAUNCH_CHECK();
   return 0;
 }

@@ -113,11 +113,24 @@ class PackedWeights:
     def __init__(self):
         self.key = None
         self.frozen = False
+        self.valid = False   # set by pack_model_weights(): the packs were just rebuilt by the model-wide launch
         self.wf = self.wd = self.bias = None
+
+    def ensure(self, weight: torch.Tensor, bias: Optional[torch.Tensor], taps_out: int):
+        cout, cin = weight.shape[0], weight.shape[1]
+        n = taps_out * cout * cin
+        if self.wf is None or self.wf.numel() != n or self.wf.device != weight.device:
+            self.wf = torch.empty(n, dtype=torch.bfloat16, device=weight.device)
+            self.wd = torch.empty(n, dtype=torch.bfloat16, device=weight.device)
+            self.bias = None if bias is None else torch.empty(cout, dtype=torch.float32, device=weight.device)
+            self.key = None
 
     def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor], training: bool = False):
         """training: this forward will be differentiated w.r.t. the weights (ctx.needs_input_grad inside the autograd
         Function — grad mode itself is off there)."""
+        if self.valid:          # rebuilt at the start of this encode()/decode() by ONE launch for all layers
+            self.valid = False
+            return self.wf, self.wd, self.bias
         key = (weight.data_ptr(), weight._version, weight.dtype, None if bias is None else (bias.data_ptr(), bias._version))
         # EVERY forward repacks (75 small kernels, ~0.4 ms per 512^2 step): fused optimizers (torch.optim.AdamW(fused=True))
         # and `.data` writes update a parameter without touching `_version`, so no host-side key can prove that the packs
@@ -153,6 +166,55 @@ def freeze_weight_packs(model: torch.nn.Module, frozen: bool = True) -> None:
             pk = getattr(m, attr, None)
             if pk is not None:
                 pk.frozen = frozen
+
+
+class PackPlan:
+    """Device-side work list of vcd_multi_pack_weights for a fixed set of layers: (weight, bias, packs, mode)."""
+
+    def __init__(self, layers):
+        import ctypes as C
+        self.layers = layers
+        self.key = self.make_key(layers)
+        dev = layers[0][0].device
+        tco, tci = _lib.lib().vcd_pack_tile_co(), _lib.lib().vcd_pack_tile_ci()
+
+        class Desc(C.Structure):
+            _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p), ("bias_f32", C.c_void_p),
+                        ("dtype", C.c_int32), ("cout", C.c_int32), ("cin", C.c_int32), ("taps", C.c_int32), ("mode", C.c_int32),
+                        ("pad_", C.c_int32)]
+        descs = (Desc * len(layers))()
+        tl, tc, ti = [], [], []
+        for i, (w, b, packs, mode) in enumerate(layers):
+            cout, cin = w.shape[0], w.shape[1]
+            taps = (w.shape[2] * w.shape[3]) if w.dim() == 4 else 1
+            packs.ensure(w, b, 16 if mode == 1 else taps)
+            if not w.is_contiguous():
+                raise _lib.VcdError("pack plan: weights must be contiguous")
+            descs[i] = Desc(w.data_ptr(), None if b is None else b.data_ptr(), packs.wf.data_ptr(), packs.wd.data_ptr(),
+                            None if packs.bias is None else packs.bias.data_ptr(), dtype_code(w), cout, cin, taps, mode, 0)
+            for co in range(0, cout, tco):
+                for ci in range(0, cin, tci):
+                    tl.append(i); tc.append(co); ti.append(ci)
+        raw = bytes(descs)
+        self.descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        self.tile_layer, self.tile_co, self.tile_ci = i32(tl), i32(tc), i32(ti)
+        self.n_tiles = len(tl)
+
+    @staticmethod
+    def make_key(layers):
+        return tuple((w.data_ptr(), w.dtype, None if b is None else b.data_ptr(), p.wf.data_ptr() if p.wf is not None else 0)
+                     for w, b, p, _ in layers)
+
+    def run(self):
+        call("vcd_multi_pack_weights", _p(self.descs), _p(self.tile_layer), _p(self.tile_co), _p(self.tile_ci), self.n_tiles, _st())
+        for _, _, packs, _ in self.layers:
+            packs.valid = True
+
+    def expire(self):
+        """end of the encode() / decode() call the packs were built for: a later direct call of a layer packs itself"""
+        for _, _, packs, _ in self.layers:
+            packs.valid = False
 
 
 def _workspace(fn: str, shape, impl: int, device):
@@ -293,9 +355,15 @@ class UpconvPackedWeights:
     def __init__(self):
         self.key = None
         self.frozen = False
+        self.valid = False
         self.wf = self.wd = self.bias = None
 
+    ensure = PackedWeights.ensure
+
     def get(self, weight: torch.Tensor, bias: Optional[torch.Tensor], training: bool = False):
+        if self.valid:
+            self.valid = False
+            return self.wf, self.wd, self.bias
         key = (weight.data_ptr(), weight._version, weight.dtype, None if bias is None else (bias.data_ptr(), bias._version))
         if key != self.key or not self.frozen or training or torch.cuda.is_current_stream_capturing():
             _require_cuda(weight, "conv weight")
@@ -379,23 +447,29 @@ class _GroupNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, groups: int, eps: float, act: bool, slot_in: Optional[TrackSlot],
-                slot_out: Optional[TrackSlot], split: bool, sole_consumer_is_conv: bool = False):
+                slot_out: Optional[TrackSlot], split: bool, sole_consumer_is_conv: bool = False,
+                slot_in_extra: Optional[TrackSlot] = None):
         x = _nhwc(x)
         N, C = x.shape[0], x.shape[-1]
         hw = x.numel() // (N * C)
         sums = pop_gn_sums(x, groups)   # always popped: an entry left behind would pin x until the next encode()
-        if slot_in is not None:
-            sums = None                 # input statistics are tracked: the statistics pass runs anyway and fills the slot
-        if sums is None:   # not produced by the epilogue of the GEMM that wrote x (or input statistics are tracked)
+        stats_in_apply = slot_in is not None and sums is not None
+        if sums is None:   # not produced by the epilogue of the GEMM that wrote x: statistics pass (+ input statistics)
             sums = torch.empty(N * groups * 2, dtype=torch.float64, device=x.device)
             call("vcd_gn_stats", _p(x), _p(sums), _p(None if slot_in is None else slot_in.raw),
                  0.0 if slot_in is None else slot_in.near_zero, N, hw, C, groups, _st())
         out = torch.empty_like(x)
         g, b = gamma.detach(), beta.detach()
+        # group sums from the producer's epilogue AND the input tracked: its per-channel statistics ride in the apply pass,
+        # which reads x anyway (no extra pass over the tensor)
+        nz = slot_out.near_zero if slot_out is not None else (slot_in.near_zero if slot_in is not None else 0.0)
         call("vcd_gn_apply_fwd", _p(x), _p(sums), _p(g), _p(b), dtype_code(g), _p(out),
-             _p(None if slot_out is None else slot_out.raw), 0.0 if slot_out is None else slot_out.near_zero,
+             _p(slot_in.raw if stats_in_apply else None), _p(None if slot_out is None else slot_out.raw), nz,
              float(eps), 1 if act else 0, N, hw, C, groups, _st())
         if slot_in is not None:
+            if slot_in_extra is not None:     # a second subscription to the same tensor (e.g. conv_in.output + norm1.input)
+                slot_in_extra.raw.copy_(slot_in.raw)
+                slot_in_extra.finalize(N * hw)
             slot_in.finalize(N * hw)
         if slot_out is not None:
             slot_out.finalize(N * hw)
@@ -434,13 +508,18 @@ class _GroupNormFn(torch.autograd.Function):
             push_colsum(dx, colsum)
         else:
             call("vcd_gn_param_grad", _p(sums), _p(dsdb), _p(dgamma), _p(dbeta), pdt, eps, N, hw, C, G, _st())
-        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
-def group_norm(x, gamma, beta, groups, eps, act, slot_in=None, slot_out=None, split=False, sole_consumer_is_conv=False):
+def group_norm(x, gamma, beta, groups, eps, act, slot_in=None, slot_out=None, split=False, sole_consumer_is_conv=False,
+               slot_in_extra=None):
     """sole_consumer_is_conv: the caller guarantees that the (first) output goes into exactly one ops.conv2d and nowhere
-    else — that conv's dgrad then performs SiLU' and the backward reduction of this GroupNorm in its epilogue."""
-    return _GroupNormFn.apply(x, gamma, beta, groups, eps, act, slot_in, slot_out, split, sole_consumer_is_conv)
+    else — that conv's dgrad then performs SiLU' and the backward reduction of this GroupNorm in its epilogue.
+    slot_in / slot_in_extra: statistics slots of the INPUT tensor (slot_in_extra receives a copy of slot_in's sums)."""
+    if slot_in is None and slot_in_extra is not None:
+        slot_in, slot_in_extra = slot_in_extra, None
+    return _GroupNormFn.apply(x, gamma, beta, groups, eps, act, slot_in, slot_out, split, sole_consumer_is_conv,
+                              slot_in_extra)
 
 
 # ------------------------------------------------------------------------------------------

@@ -91,6 +91,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
                 "g_host": [torch.zeros(T, dtype=torch.int64).pin_memory() for _ in range(4)],
                 "g_ptrs": None, "turn": 0,
                 "sqnorm": torch.zeros(1, dtype=torch.float64, device=dev),
+                "steps_dev": torch.zeros(T, dtype=torch.int32, device=dev), "uniform": True,
             }
             groups.append((g, tab))
         self._tables = groups
@@ -144,13 +145,24 @@ class FusedClipAdamW(torch.optim.Optimizer):
             self._refresh_grad_table(tab)
             b1, b2 = g["betas"]
             clip = self._pending_clip if self._pending_clip is not None else 0.0
+            # torch counts steps per parameter (a parameter without a gradient is skipped and lags behind); the table
+            # only travels to the device once the counters have diverged — never in the reference's training loop
+            steps = []
+            for p in tab["params"]:
+                st = self.state[p]
+                if p.grad is not None:
+                    st["step"] = int(st["step"]) + 1
+                steps.append(int(st["step"]))
+            tab["uniform"] = tab["uniform"] and all(s == steps[0] for s in steps)
+            steps_ptr = None
+            if not tab["uniform"]:
+                tab["steps_dev"].copy_(torch.tensor(steps, dtype=torch.int32))
+                steps_ptr = tab["steps_dev"].data_ptr()
             with torch.cuda.device(tab["device"]):
                 call("vcd_clip_adamw_step", tab["p"].data_ptr(), tab["g"].data_ptr(), tab["m"].data_ptr(), tab["v"].data_ptr(),
                      tab["numel"].data_ptr(), tab["dtype"].data_ptr(), tab["chunk_tensor"].data_ptr(),
                      tab["chunk_off"].data_ptr(), tab["n_chunks"], tab["sqnorm"].data_ptr() if clip > 0 else None,
                      float(clip), float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
-                     int(self._steps), _st())
-            for p in tab["params"]:
-                self.state[p]["step"] = self._steps
+                     steps_ptr, max(1, steps[0]), _st())
         self._pending_clip = None
         return loss

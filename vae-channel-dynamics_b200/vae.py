@@ -66,6 +66,9 @@ class B200Conv2d(nn.Conv2d):
         self._packs = ops.PackedWeights()
         self._track_out: Optional[ops.TrackSlot] = None
         self._gn_groups = 0   # > 0: the output feeds a GroupNorm of that many groups (sums fused into the epilogue)
+        # the GroupNorm whose INPUT is exactly this conv's output (conv_in -> first norm1, conv1 -> norm2): a statistics
+        # slot on this conv's output is then filled by that GroupNorm's own pass over the tensor (no extra read)
+        self._stats_consumer = None
 
     def forward(self, x, residual=None):
         xp = ops.to_nhwc(x)
@@ -80,7 +83,15 @@ class B200Conv2d(nn.Conv2d):
                        gn_groups=0 if _hooked(self) else self._gn_groups)
         out = _logi(y)
         if self._track_out is not None:
-            ops.chan_stats(out.detach(), self._track_out)
+            cons = self._stats_consumer[0] if self._stats_consumer is not None else None
+            if cons is not None and residual is None and not _hooked(self):
+                # the reference's buffer is keyed in first-fire order (monitor.py:101): this target fires HERE, even though
+                # its statistics are produced a moment later by the consuming GroupNorm's pass over the same tensor
+                if self._track_out.on_finalize is not None:
+                    self._track_out.on_finalize()
+                cons._pending_in = (self._track_out, y.data_ptr())
+            else:
+                ops.chan_stats(out.detach(), self._track_out)
         return out
 
 
@@ -93,8 +104,15 @@ class B200GroupNorm(nn.GroupNorm):
         self._track_out: Optional[ops.TrackSlot] = None
 
     def forward(self, x, act: bool = False, split: bool = False, feeds_conv_only: bool = False):
-        y = ops.group_norm(_phys(x), self.weight, self.bias, self.num_groups, self.eps, act,
-                           self._track_in, self._track_out, split, feeds_conv_only)
+        xp = _phys(x)
+        extra, pend = None, self.__dict__.pop("_pending_in", None)
+        if pend is not None:
+            if pend[1] == xp.data_ptr():          # the producing conv's output really is this input tensor
+                extra = pend[0]
+            else:                                  # cannot happen through this module tree: never lose statistics silently
+                raise VcdError("statistics hand-off: the tracked conv output is not the input of its GroupNorm")
+        y = ops.group_norm(xp, self.weight, self.bias, self.num_groups, self.eps, act,
+                           self._track_in, self._track_out, split, feeds_conv_only, slot_in_extra=extra)
         if split:   # (normalised, input routed through for the block's skip connection)
             return _logi(y[0]), _logi(y[1])
         return _logi(y)
@@ -377,10 +395,13 @@ class B200AutoencoderKL(nn.Module):
         def block(resnets, sampler):
             for i, r in enumerate(resnets):
                 r.conv1._gn_groups = g
+                r.conv1._stats_consumer = (r.norm2,)      # tuple: not registered as a child module of the conv
                 if sampler is None or i < len(resnets) - 1:
                     r.conv2._gn_groups = g
             if sampler is not None:
                 sampler.conv._gn_groups = g
+        self.encoder.conv_in._stats_consumer = (self.encoder.down_blocks[0].resnets[0].norm1,)
+        self.decoder.conv_in._stats_consumer = (self.decoder.mid_block.resnets[0].norm1,)
         for net in (self.encoder, self.decoder):
             net.conv_in._gn_groups = g
             blocks = net.down_blocks if net is self.encoder else net.up_blocks
@@ -399,19 +420,62 @@ class B200AutoencoderKL(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    # ---- GEMM operand packs: one launch per forward for ALL layers -----------------------------------------
+    def _pack_layers(self, root: nn.Module):
+        up_convs = {id(m.conv): m for m in root.modules() if isinstance(m, Upsample2D)}
+        layers = []
+        for m in root.modules():
+            if isinstance(m, (B200Conv2d, B200Linear)):
+                up = up_convs.get(id(m))
+                if up is not None and ops.upconv_supported(m.in_channels, m.out_channels):
+                    layers.append((m.weight, m.bias, up._up_packs, 1))       # phase-form packs of the fused Upsample2D path
+                else:
+                    layers.append((m.weight, m.bias, m._packs, 0))
+        return layers
+
+    def _pack_weights(self, which: str):
+        """Rebuild the bf16 operand packs of every conv / linear layer of the encoder (+ quant_conv) or the decoder
+        (+ post_quant_conv) in ONE kernel launch (they are rebuilt on every forward: fused optimizers update parameters
+        without bumping `_version`, ops.PackedWeights).  Returns the plan; its packs are valid until plan.expire().
+        Layers that take an unfused path (a hooked Upsample2D conv) find their own pack not valid and pack themselves."""
+        cache = self.__dict__.setdefault("_pack_layer_cache", {})
+        ck = (which, ops.get_conv_impl())
+        if ck not in cache:          # the module tree is fixed; which Upsample2D convs use the phase form depends on the impl
+            roots = [self.encoder, self.quant_conv] if which == "encoder" else [self.decoder, self.post_quant_conv]
+            cache[ck] = [l for r in roots for l in self._pack_layers(r)]
+        layers = cache[ck]
+        if not layers or not layers[0][0].is_cuda:
+            return None
+        plans = self.__dict__.setdefault("_pack_plans", {})
+        plan = plans.get(ck)
+        if plan is None or plan.key != ops.PackPlan.make_key(layers):
+            plan = plans[ck] = ops.PackPlan(layers)
+        plan.run()
+        return plan
+
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         if x.dim() != 4:
             raise VcdError(f"encode expects [N, 3, H, W], got {tuple(x.shape)}")
         self._sync_gamma_if_pending()
         ops.clear_colsums()
-        moments = self.quant_conv(self.encoder(x))
+        plan = self._pack_weights("encoder") if x.is_cuda else None
+        try:
+            moments = self.quant_conv(self.encoder(x))
+        finally:
+            if plan is not None:
+                plan.expire()
         dist = DiagonalGaussianDistribution(moments)
         return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True):
         if not torch.is_grad_enabled():
             ops.clear_colsums()     # decode-only loops (wrapper.decode, logit lens): drop stale producer->consumer hand-offs
-        y = self.decoder(self.post_quant_conv(z))          # logical [N, 3, H, W] bf16
+        plan = self._pack_weights("decoder") if z.is_cuda else None
+        try:
+            y = self.decoder(self.post_quant_conv(z))          # logical [N, 3, H, W] bf16
+        finally:
+            if plan is not None:
+                plan.expire()
         sample = ops.to_nchw(_phys(y), self.output_dtype)  # contiguous NCHW, fp32
         sample._vcd_nhwc = _phys(y)                        # fused-loss fast path (vcd_b200.losses)
         return SimpleNamespace(sample=sample) if return_dict else (sample,)
