@@ -568,7 +568,9 @@ def main():
     plant_dead_channels(wrapper.vae, torch)
     model = wrapper
     if world > 1 and not args.graph:
-        model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[local_rank], gradient_as_bucket_view=True)
+        bucket_mb = float(os.environ.get("VCD_BENCH_BUCKET_MB", "25"))       # torch's default bucket_cap_mb
+        model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[local_rank], gradient_as_bucket_view=True,
+                                                          bucket_cap_mb=bucket_mb)
     # exactly the constructor call of train.py:184-187 (no fused= flag: torch picks its foreach implementation on CUDA) ...
     torch_opt = torch.optim.AdamW(wrapper.parameters(), lr=5e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8,
                                   **({"fused": True} if args.optimizer == "torch-fused" else {}))
@@ -641,6 +643,10 @@ def main():
 
     def timed(K, e2e):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if os.environ.get("VCD_BENCH_NOGC"):       # experiment knob: is a Python GC pause visible in the step time?
+            import gc
+            gc.collect()
+            gc.disable()
         barrier()
         l0 = vcd_b200._lib.launches
         e0.record()
@@ -777,7 +783,9 @@ def main():
 
 def write_kernel_table(torch, path, train_step, resident):
     from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    hostgap = bool(os.environ.get("VCD_BENCH_HOSTGAP"))      # profiling aid: what does the HOST do during the largest device gap?
+    acts = [ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if hostgap else [])
+    with profile(activities=acts) as prof:
         for i in range(2):
             train_step(resident[i % len(resident)])
         torch.cuda.synchronize()
@@ -792,9 +800,23 @@ def write_kernel_table(torch, path, train_step, resident):
             c = gaps.setdefault(k, [0, 0.0])
             c[0] += 1
             c[1] += g
-    rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+    host_lines = []
+    if hostgap:
+        big = sorted(((b.time_range.start - a.time_range.end, a, b) for a, b in zip(evs, evs[1:])), key=lambda t: -t[0])[:3]
+        cpu = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU]
+        for g, a, b in big:
+            t0, t1 = a.time_range.end, b.time_range.start
+            inside = sorted((e for e in cpu if e.time_range.end > t0 and e.time_range.start < t1),
+                            key=lambda e: -(min(e.time_range.end, t1) - max(e.time_range.start, t0)))[:14]
+            host_lines.append(f"gap {g:.0f} us between {a.name[:40]} and {b.name[:40]}: host events overlapping it")
+            for e in inside:
+                ov = min(e.time_range.end, t1) - max(e.time_range.start, t0)
+                host_lines.append(f"    {ov:8.0f} us of {e.time_range.end - e.time_range.start:8.0f} us  {e.name[:90]}")
+    rows = sorted((e for e in prof.key_averages() if e.device_time_total > 0), key=lambda e: -e.device_time_total)
     tot = sum(e.device_time_total for e in rows)
     with open(path, "w") as f:
+        for l in host_lines:
+            f.write(l + "\n")
         f.write(f"2 steps, {tot / 2e3:.2f} ms of device time per step (torch.profiler / CUPTI, warm, in-pipeline)\n")
         f.write(f"{'ms/step':>9} {'share':>6} {'n/step':>7}  kernel\n")
         for e in rows[:45]:

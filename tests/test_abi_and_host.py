@@ -176,3 +176,47 @@ def test_groupnorm_producers_are_marked(vcd):
     assert "encoder.mid_block.attentions.0.to_out.0" in marked and "encoder.mid_block.attentions.0.to_q" not in marked
     # one producer per GroupNorm: 52 GroupNorms, 52 marked producers
     assert len(marked) == sum(1 for mod in m.modules() if isinstance(mod, nn.GroupNorm))
+
+
+def test_from_pretrained_reads_legacy_sdxl_vae_checkpoints(tmp_path):
+    """SURVEY 8f-3 / train.py:412, evaluate.py:99: the published stabilityai/sdxl-vae file predates diffusers' attention
+    refactor — its mid-block attention parameters are named query / key / value / proj_attn ([upstream] diffusers converts
+    them on load), and older exports store them as 1x1 convolutions [C, C, 1, 1].  A directory in that layout must load
+    into the same module tree, and save_pretrained must write the modern diffusers names back."""
+    import json
+
+    import torch
+    from safetensors.torch import load_file, save_file
+    import vcd_b200
+    torch.manual_seed(3)
+    vae = vcd_b200.B200AutoencoderKL()
+    sd = {k: v.detach().clone() for k, v in vae.state_dict().items()}
+    legacy = {}
+    ren = {".to_q.": ".query.", ".to_k.": ".key.", ".to_v.": ".value.", ".to_out.0.": ".proj_attn."}
+    n_renamed = 0
+    for k, v in sd.items():
+        nk = k
+        for new, old in ren.items():
+            if new in k:
+                nk = k.replace(new, old)
+                n_renamed += 1
+                if k.endswith(".weight"):
+                    v = v[:, :, None, None].contiguous()          # Linear [C, C] stored as a 1x1 conv
+        legacy[nk] = v
+    assert n_renamed == 16 and not any(".to_q." in k for k in legacy)
+    d = tmp_path / "legacy_vae"
+    d.mkdir()
+    save_file(legacy, str(d / "diffusion_pytorch_model.safetensors"), metadata={"format": "pt"})
+    cfg = dict(vcd_b200.vae.SDXL_VAE_CONFIG, _diffusers_version="0.18.0.dev0", _name_or_path="stabilityai/sdxl-vae")
+    (d / "config.json").write_text(json.dumps(cfg))
+    loaded = vcd_b200.B200AutoencoderKL.from_pretrained(str(d))
+    for k, v in loaded.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    assert loaded.config.scaling_factor == 0.13025 and loaded.config["_class_name"] == "AutoencoderKL"
+    half = vcd_b200.B200AutoencoderKL.from_pretrained(str(d), torch_dtype=torch.bfloat16)
+    assert half.dtype == torch.bfloat16
+    out = tmp_path / "resaved"
+    loaded.save_pretrained(str(out))
+    again = load_file(str(out / "diffusion_pytorch_model.safetensors"))
+    assert set(again) == set(sd) and all(torch.equal(again[k], sd[k]) for k in sd)
+    assert json.loads((out / "config.json").read_text())["block_out_channels"] == [128, 256, 512, 512]

@@ -149,6 +149,42 @@ def test_fused_channel_stats_match_monitor_formula(vcd):
         assert rel_err(run[4] / F_, (t.abs() < 0.05).float().mean(dim=[0, 2, 3])) < 1e-4 + 1e-9
 
 
+@pytest.mark.parametrize("act,tau,C,H,W", [(True, 0.05, 128, 16, 16), (False, 0.0, 256, 9, 7), (True, 0.0, 512, 8, 8),
+                                             (True, 0.05, 128, 64, 64)])
+def test_input_and_output_statistics_in_one_apply_pass(vcd, act, tau, C, H, W):
+    """The group sums come from the producing GEMM's epilogue (here: pushed by hand), so the statistics pass does not run:
+    vcd_gn_apply_fwd then fills BOTH slots in its single pass over x — the input slot directly, the output slot's sum /
+    sum of squares derived from the input sums (y is affine in x per image and channel), its |y| sum, max and near-zero
+    count accumulated.  All five rows of both slots against torch."""
+    ops = vcd.ops
+    N, G = 3, 32
+    x = bf16_round(torch.randn(N, C, H, W, device="cuda") * 1.5 + 0.2)
+    gamma = torch.rand(C, device="cuda") + 0.1
+    beta = torch.randn(C, device="cuda") * 0.1
+    xp = nhwc(x)
+    xg = x.reshape(N, G, -1).double()
+    sums = torch.stack([xg.sum(-1), (xg * xg).sum(-1)], dim=-1).reshape(-1).contiguous()       # [N][G][2] fp64
+    s_in, s_out, s_extra = ops.TrackSlot(C, "cuda", tau), ops.TrackSlot(C, "cuda", tau), ops.TrackSlot(C, "cuda", tau)
+    l0 = vcd._lib.launches
+    ops.push_gn_sums(xp, sums, G)
+    out = ops.group_norm(xp, gamma, beta, G, 1e-6, act, s_in, s_out, slot_in_extra=s_extra)
+    assert vcd._lib.launches - l0 == 1 + 3          # one apply launch + three finalize launches: no vcd_gn_stats
+    y = F.group_norm(x, G, gamma, beta, 1e-6)
+    assert rel_err(nchw(out), F.silu(y) if act else y) < TOL
+    n = N * H * W
+    for slot, t in ((s_in, x), (s_extra, x), (s_out, y)):
+        run = slot.run.view(5, C)
+        assert float(slot.scal[2]) == 1.0
+        assert rel_err(run[0], t.abs().mean(dim=[0, 2, 3])) < 1e-4                       # mean |.|   (monitor.py:64-67)
+        assert rel_err(run[1], t.mean(dim=[0, 2, 3])) < 1e-4                             # mean
+        assert rel_err(run[2], t.var(dim=[0, 2, 3], unbiased=False)) < 2e-4              # variance
+        assert rel_err(run[3], t.abs().amax(dim=[0, 2, 3])) < 1e-6                       # max |.|
+        if tau > 0:
+            assert rel_err(run[4], (t.abs() < tau).float().mean(dim=[0, 2, 3])) < 1e-4 + 2.0 / n
+        assert abs(float(slot.scal[0]) - float(t.mean())) < 1e-4 * max(1.0, abs(float(t.mean())))
+        assert abs(float(slot.scal[1]) - float(t.std())) < 1e-4 * float(t.std())
+
+
 def test_chan_stats_standalone_layouts(vcd):
     ops = vcd.ops
     t = torch.randn(3, 24, 7, 9, device="cuda")

@@ -40,6 +40,8 @@ void vcd_set_error(const char* fmt, ...);
 static inline cudaStream_t as_stream(vcd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int vcd_num_sms();
+// per-DEVICE one-time flags (cudaFuncSetAttribute applies to the current device's context only): slot in [0, 16)
+bool* vcd_device_once(int slot);
 
 // ---- device helpers ---------------------------------------------------------------
 // eight bf16 values moved as ONE 128-bit access (LDG.E.128 / STG.E.128; a struct of bfloat162 is split

@@ -18,6 +18,12 @@ void vcd_set_error(const char* fmt, ...) {
 }
 extern "C" const char* vcd_last_error(void) { return g_err; }
 extern "C" int vcd_version(void) { return 100; }
+bool* vcd_device_once(int slot) {
+  static bool flags[64][16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &flags[dev & 63][slot & 15];
+}
 int vcd_num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -801,14 +807,8 @@ extern "C" int vcd_upconv2d_wgrad(const void* x, const void* dy_planes, void* dw
   int rc;
   upconv_wgrad_combine_kernel<<<ew_blocks(main_elems), 256, 0, st>>>(acc16, wsf, Cout, Cin);
   VCD_LAUNCH_CHECK();
-  if (db) {
-    if (db_colsum) {
-      VCD_CUDA(cudaMemcpyAsync(wsf + main_elems, db_colsum, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    } else if ((rc = conv_bias_grad(dy_planes, wsf + main_elems, (int64_t)N * 4 * H * W, Cout, st))) {
-      return rc;
-    }
-  }
-  return conv_wgrad_finalize(wsf, dw, db, dtype, Cout, Cin, 9, st);
+  if (db && !db_colsum && (rc = conv_bias_grad(dy_planes, wsf + main_elems, (int64_t)N * 4 * H * W, Cout, st))) return rc;
+  return conv_wgrad_finalize(wsf, db ? db_colsum : nullptr, dw, db, dtype, Cout, Cin, 9, st);
 }
 
 extern "C" int vcd_conv_umma_supported(int Cin, int Cout, int KH, int KW, int stride) {
@@ -978,14 +978,8 @@ extern "C" int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* d
     rc = simt_conv_wgrad(x, dy, wsf, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, st);
   }
   if (rc) return rc;
-  if (db) {
-    if (db_colsum) {
-      VCD_CUDA(cudaMemcpyAsync(wsf + main_elems, db_colsum, Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    } else if ((rc = conv_bias_grad(dy, wsf + main_elems, (int64_t)N * Ho * Wo, Cout, st))) {
-      return rc;
-    }
-  }
-  return conv_wgrad_finalize(wsf, dw, db, dtype, Cout, Cin, taps, st);
+  if (db && !db_colsum && (rc = conv_bias_grad(dy, wsf + main_elems, (int64_t)N * Ho * Wo, Cout, st))) return rc;
+  return conv_wgrad_finalize(wsf, db ? db_colsum : nullptr, dw, db, dtype, Cout, Cin, taps, st);
 }
 
 // D[b][m][n] = alpha * sum_k A[b][m][k] B[(b)][n][k] (+bias[n]) (+residual[b][m][n])

@@ -10,6 +10,7 @@ int simt_conv_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int 
 int simt_conv_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                     int stride, int pad_t, int pad_l, int Ho, int Wo, cudaStream_t st);
 int conv_bias_grad(const void* dy, float* out, int64_t pixels, int C, cudaStream_t st);
-int conv_wgrad_finalize(const float* ws, void* dw, void* db, int dtype, int Cout, int Cin, int taps, cudaStream_t st);
+int conv_wgrad_finalize(const float* ws, const float* bias_src, void* dw, void* db, int dtype, int Cout, int Cin, int taps,
+                        cudaStream_t st);
 int gn_make_ab(const double* sums, const void* gamma, const void* beta, int pdt, float eps, int N, int HW, int C, int G,
                float* ab, cudaStream_t st);

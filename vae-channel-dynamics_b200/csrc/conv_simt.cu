@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
 }
 
 // ws [tap][Co][Ci] fp32 (+ bias ws [Co]) -> OIHW dw / db in the parameter dtype
-__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, void* __restrict__ dw, void* __restrict__ db, int dt,
-                                      int Co, int Ci, int taps) {
+__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ bias_src,
+                                      void* __restrict__ dw, void* __restrict__ db, int dt, int Co, int Ci, int taps) {
   int64_t total = (int64_t)Co * Ci * taps;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int t = (int)(i % taps);
@@ -297,7 +297,7 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ ws, void* __rest
   }
   if (db)
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Co; i += (int64_t)gridDim.x * blockDim.x)
-      store_param(db, dt, i, ws[total + i]);
+      store_param(db, dt, i, bias_src[i]);
 }
 
 Taps make_taps(int KH, int KW, int pad_t, int pad_l, bool dgrad) {
@@ -406,9 +406,12 @@ int conv_bias_grad(const void* dy, float* out, int64_t pixels, int C, cudaStream
   return 0;
 }
 
-int conv_wgrad_finalize(const float* ws, void* dw, void* db, int dtype, int Cout, int Cin, int taps, cudaStream_t st) {
+// bias_src: fp32 [Cout] bias gradient (the column sums a previous kernel already produced), or NULL = ws + taps*Cout*Cin
+int conv_wgrad_finalize(const float* ws, const float* bias_src, void* dw, void* db, int dtype, int Cout, int Cin, int taps,
+                        cudaStream_t st) {
   int64_t total = (int64_t)Cout * Cin * taps;
-  wgrad_finalize_kernel<<<grid_for(total, 256), 256, 0, st>>>(ws, dw, db, dtype, Cout, Cin, taps);
+  wgrad_finalize_kernel<<<grid_for(total, 256), 256, 0, st>>>(ws, bias_src ? bias_src : ws + total, dw, db, dtype, Cout, Cin,
+                                                             taps);
   VCD_LAUNCH_CHECK();
   return 0;
 }

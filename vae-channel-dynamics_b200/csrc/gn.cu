@@ -87,11 +87,15 @@ struct Stat5 {
 #pragma unroll
     for (int j = 0; j < 4; ++j) s[j] = q[j] = sa[j] = mx[j] = nz[j] = 0ull;
   }
-  template <bool NZ>
+  // LINEAR: sum and sum of squares are NOT accumulated — the caller derives them from another Stat5 of an affinely
+  // related stream (y = A x + B per thread-channel: sum y = A sum x + B n, sum y^2 = A^2 sum x^2 + 2AB sum x + B^2 n)
+  template <bool NZ, bool LINEAR = false>
   __device__ __forceinline__ void add(int j, f32x2 y, float tau) {
     const f32x2 a = abs2(y);
-    s[j] = add2(s[j], y);
-    q[j] = fma2(y, y, q[j]);
+    if (!LINEAR) {
+      s[j] = add2(s[j], y);
+      q[j] = fma2(y, y, q[j]);
+    }
     sa[j] = add2(sa[j], a);
     mx[j] = max2(mx[j], a);
     if (NZ) {   // the near-zero count is compiled in only when a threshold is configured (tau > 0)
@@ -239,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, (SIN || SOUT) ? 2 : 3) gn_apply_kern
   const int64_t base = (int64_t)n * HW * C + m.c0;
   // bytes in flight per SM: 3 blocks x 256 threads x 4 x 16 B = 48 KB without statistics; the statistics variants hold 40-80
   // accumulator registers, run 2 blocks per SM and keep 6 (4 with both slots) loads in flight per thread instead
-  constexpr int U = (SIN && SOUT) ? 4 : ((SIN || SOUT) ? 6 : kUnroll);
+  constexpr int U = (SIN || SOUT) ? 6 : kUnroll;
+  float npix = 0.f;   // pixels this thread processed (SIN && SOUT: output sums are derived from the input sums)
   for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
     bf16x8 v[U];
 #pragma unroll
@@ -257,10 +262,21 @@ __global__ void __launch_bounds__(kThreads, (SIN || SOUT) ? 2 : 3) gn_apply_kern
       for (int j = 0; j < 4; ++j) {
         if (SIN) sin.add<NZ>(j, f[j], near_zero);
         const f32x2 w = fma2(ka[j], f[j], kb[j]);       // ACT: u = y/2, else y
-        if (SOUT) sout.add<NZ>(j, ACT ? add2(w, w) : w, near_zero);
+        if (SOUT) sout.add<NZ, SIN && SOUT>(j, ACT ? add2(w, w) : w, near_zero);
         f[j] = ACT ? fma2(w, tanh2(w), w) : w;           // silu(y) = u + u*tanh(u)
       }
       st8(out + base + p * C, pack8x(f));
+      if (SIN && SOUT) npix += 1.f;
+    }
+  }
+  if (SIN && SOUT) {
+    const f32x2 two = dup2(ACT ? 2.f : 1.f), n2 = dup2(npix);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const f32x2 A = mul2(ka[j], two), B = mul2(kb[j], two);          // y = A x + B (ka, kb are halved under ACT)
+      sout.s[j] = fma2(A, sin.s[j], mul2(B, n2));
+      const f32x2 AB2 = mul2(mul2(A, B), dup2(2.f));
+      sout.q[j] = fma2(mul2(A, A), sin.q[j], fma2(AB2, sin.s[j], mul2(mul2(B, B), n2)));
     }
   }
   if (SIN) flush_stat5(sin, sm, m, cstats_in, C);

@@ -355,7 +355,7 @@ int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaPara
   int grid = p.total_tiles < vcd_num_sms() ? p.total_tiles : vcd_num_sms();
   if (grid <= 0) return 0;
   if (block_n == 256) {
-    static bool attr = false;
+    bool& attr = *vcd_device_once(0);
     if (!attr) {
       VCD_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg<256>::kSmemBytes));
@@ -363,7 +363,7 @@ int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaPara
     }
     umma_gemm_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(mapA, mapB, p);
   } else if (block_n == 128) {
-    static bool attr = false;
+    bool& attr = *vcd_device_once(1);
     if (!attr) {
       VCD_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg<128>::kSmemBytes));

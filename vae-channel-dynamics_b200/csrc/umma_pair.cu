@@ -17,6 +17,14 @@
 #include "umma_pair.cuh"
 #include "umma_ptx.cuh"
 
+// Profiling knobs (skip MMAs / stores / B traffic) exist only in a -DVCD_PAIR_DEBUG build: in the product library the
+// macro is the constant 0 and the branches vanish from the MMA / TMA loops.
+#ifdef VCD_PAIR_DEBUG
+#define VCD_PAIR_DBG(p, bit) (((p).dbg & (bit)) != 0)
+#else
+#define VCD_PAIR_DBG(p, bit) (false)
+#endif
+
 namespace {
 using namespace umma;
 
@@ -220,7 +228,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int nt_here = min(C::kTapsPerStage, p.g_tap0[g + 1] - tap);
             mbar_wait(bempty(sb), pb ^ 1u);
             if (elect_one_sync()) {
-              if (p.dbg & 8) {  // profiling aid: no B traffic (stale shared memory is multiplied)
+              if (VCD_PAIR_DBG(p, 8)) {  // profiling aid: no B traffic (stale shared memory is multiplied)
                 if (rank == 0) mbar_arrive(bfull(sb));
               } else {
                 if (rank == 0) mbar_arrive_expect_tx(bfull(sb), 2u * (uint32_t)(nt_here * C::kTapBytes));
@@ -285,7 +293,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const uint32_t b0 = b_base + sb * C::kBBytes + u * C::kTapBytes;
                 const uint32_t a_lo = ((a0 >> 4) & 0x3FFFu) | (1u << 16);
                 const uint32_t b_lo = ((b0 >> 4) & 0x3FFFu) | (1u << 16);
-                if (!(p.dbg & 2)) {
+                if (!VCD_PAIR_DBG(p, 2)) {
                   // K advances 16 bf16 = 32 B (descriptor units of 16 B: +2) inside the 128-byte swizzle row
                   umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
                   umma_bf16_pair(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2), ((uint64_t)b_hi << 32) | (b_lo + 2), p.idesc, 1u);
@@ -368,7 +376,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int col0 = nt * BLOCK_N + ch * 32;
         // full chunk of an 8-element-aligned tensor: the 32 x 64 B block goes through shared memory so that every
         // global store instruction writes 8 rows x 64 contiguous bytes (whole sectors) instead of 32 rows x 16 B
-        const bool staged = (p.Nout & 7) == 0 && col0 + 32 <= p.Nout && !(p.dbg & 16);
+        const bool staged = (p.Nout & 7) == 0 && col0 + 32 <= p.Nout && !VCD_PAIR_DBG(p, 16);
         float gv[GNB ? 1 : 16];
         if (!GNB) {
 #pragma unroll
@@ -379,7 +387,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = xs[j] = 0.f;
         }
-        if (valid && col0 < p.Nout && !(p.dbg & 4)) {
+        if (valid && col0 < p.Nout && !VCD_PAIR_DBG(p, 4)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
           if constexpr (GNB) {  // v = dL/d act(GN(x)) -> g = v * SiLU'(a x + b)
@@ -451,7 +459,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int j = 0; j < 32; ++j) xs[j] *= v[j];
           }
         }
-        if (staged && tc.valid && !(p.dbg & 4)) {  // warp-uniform
+        if (staged && tc.valid && !VCD_PAIR_DBG(p, 4)) {  // warp-uniform
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -484,7 +492,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
       };
-      if (!(p.dbg & 1)) {
+      if (!VCD_PAIR_DBG(p, 1)) {
         constexpr int NCH = BLOCK_N / 64;  // chunks per warp
         const int ch0 = chalf * NCH;
 #pragma unroll 1
@@ -801,17 +809,20 @@ int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p,
   if (p.total_items <= 0) return 0;
   ++g_pair_launches;
   {
+#ifdef VCD_PAIR_DEBUG
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("VCD_PAIR_DBG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
+#else
+    p.dbg = 0;
+#endif
   }
   const int max_clusters = vcd_num_sms() / 2;
   const int clusters = p.total_items < max_clusters ? p.total_items : max_clusters;
   const int grid = clusters * 2;
   const bool gnb = p.gnb_x != nullptr;
-  static bool attr_set[4] = {false, false, false, false};
   auto launch = [&](auto kernel, int smem) -> int {
-    bool& done = attr_set[(block_n == 256 ? 2 : 0) + (gnb ? 1 : 0)];
+    bool& done = *vcd_device_once(2 + (block_n == 256 ? 2 : 0) + (gnb ? 1 : 0));
     if (!done) {
       VCD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       done = true;
@@ -844,19 +855,19 @@ int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgra
             ((256u >> 4) << 24);
   const int max_clusters = vcd_num_sms() / 2;
   const int grid = 2 * (p.total_items < max_clusters ? p.total_items : max_clusters);
-  static bool attr_set[2] = {false, false};
+  bool* attr_set[2] = {vcd_device_once(6), vcd_device_once(7)};
   if (block_n == 256) {
-    if (!attr_set[0]) {
+    if (!*attr_set[0]) {
       VCD_CUDA(cudaFuncSetAttribute(umma_pair_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     WCfg<256>::kSmemBytes));
-      attr_set[0] = true;
+      *attr_set[0] = true;
     }
     umma_pair_wgrad_kernel<256><<<grid, kThreads, WCfg<256>::kSmemBytes, st>>>(mapA, mapB, p);
   } else if (block_n == 128) {
-    if (!attr_set[1]) {
+    if (!*attr_set[1]) {
       VCD_CUDA(cudaFuncSetAttribute(umma_pair_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     WCfg<128>::kSmemBytes));
-      attr_set[1] = true;
+      *attr_set[1] = true;
     }
     umma_pair_wgrad_kernel<128><<<grid, kThreads, WCfg<128>::kSmemBytes, st>>>(mapA, mapB, p);
   } else {
