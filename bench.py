@@ -463,6 +463,7 @@ def instep_rooflines(torch, vcd, train_step, batches, steps, peaks):
     step.  roofline (tensor): executed FLOPs of all implicit-GEMM entry points / their summed durations; roofline_hbm:
     algorithmic bytes of the GroupNorm entry points / their durations, per kernel family."""
     lib = vcd._lib
+    vcd.ops.wgrad_side_stream_enabled = False   # two concurrently running kernels would each be charged the other's time
     float(train_step(batches[0]))          # one untimed step with the hook installed (event pool warm-up)
     torch.cuda.synchronize()
     lib.profile = []
@@ -470,6 +471,7 @@ def instep_rooflines(torch, vcd, train_step, batches, steps, peaks):
         float(train_step(batches[i % len(batches)]))
     torch.cuda.synchronize()
     rec, lib.profile = lib.profile, None
+    vcd.ops.wgrad_side_stream_enabled = True
     by = {}
     for name, args, e0, e1 in rec:
         # integer arguments without device pointers (>= 2^31) and without the trailing stream handle
@@ -514,7 +516,8 @@ def instep_rooflines(torch, vcd, train_step, batches, steps, peaks):
             "kernel": "umma_pair_kernel / umma_pair_wgrad_kernel / umma_gemm_kernel behind the conv / upconv / gemm entry points "
                       "(entry-point durations include their memsets, finalize and colsum kernels); EXECUTED FLOPs (Upsample2D "
                       "convs run as four 2x2 phase convolutions = 16/36 of the reference formulation)",
-            "how": f"CUDA events around every C-ABI call on its launching stream, {steps} training steps in the pipeline",
+            "how": f"CUDA events around every C-ABI call on its launching stream, {steps} training steps in the pipeline "
+                   f"(weight-gradient kernels kept on the main stream for these steps so that no two timed kernels overlap)",
             "ms_per_step": tt / steps, "tflop_per_step": tf / steps / 1e12,
             "by_entry_point": {n: {"calls_per_step": v[0] / steps, "ms_per_step": v[1] / steps, "tflops": v[2] / v[1] / 1e9}
                                for n, v in sorted(tens.items())}}
@@ -812,7 +815,8 @@ def write_kernel_table(torch, path, train_step, resident):
             for e in inside:
                 ov = min(e.time_range.end, t1) - max(e.time_range.start, t0)
                 host_lines.append(f"    {ov:8.0f} us of {e.time_range.end - e.time_range.start:8.0f} us  {e.name[:90]}")
-    rows = sorted((e for e in prof.key_averages() if e.device_time_total > 0), key=lambda e: -e.device_time_total)
+    rows = sorted((e for e in prof.key_averages() if e.device_time_total > 0 and e.device_type == torch.autograd.DeviceType.CUDA),
+                  key=lambda e: -e.device_time_total)
     tot = sum(e.device_time_total for e in rows)
     with open(path, "w") as f:
         for l in host_lines:

@@ -161,3 +161,34 @@ def test_unchanged_train_py_bf16_nudge_config_with_fused_optimizer(vcd, tmp_path
         # the reference's evaluate.py cannot run a bf16 config in EITHER arm: evaluate.py:97 does getattr(torch, "bf16")
         evaluate=False)
     assert [r.split(",")[0] for r in res["intervention_history"]] == ["20", "40"]
+
+
+def test_unchanged_train_py_on_two_ranks(vcd, tmp_path):
+    """torchrun --nproc-per-node 2 launch.py train.py (needs 2 GPUs): the accelerate surface at world size 2 — DDP wrap,
+    per-rank batch sharding, the three loss all-gathers of train.py:292-294, rank-0-only classifier / nudger / CSV
+    writers — with the drop-in's global-batch statistics and gamma re-broadcast.  The run must finish, intervene on the
+    planted channels at steps 20 and 40, and save a model whose nudged scales moved."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    if rh.reference_dir() is None:
+        pytest.skip("baseline/_ref is missing: run __graft_entry__.build() where /root/reference exists")
+    wd = str(tmp_path)
+    init = _prepare_workdir(vcd, wd, n_train=96, n_test=16)
+    cfg = rh.make_config(wd, "experiment_cifar10_test.yaml", {
+        "output_dir": os.path.join(wd, "results_b200_2gpu"), "model": {"pretrained_vae_name": init},
+        "data": {"max_samples": 96, "validation_max_samples": 16},           # 96 / (8 per rank x 2 ranks) = 6 steps per epoch
+        "training": {"num_train_epochs": 8}}, "two_ranks.yaml")
+    log = rh.run_script("b200", "train.py", ["--config_path", cfg], wd, nproc=2)
+    assert "Training finished." in log
+    out = os.path.join(wd, "results_b200_2gpu", "sdxl_vae_cifar10_test_run")
+    hist = open(os.path.join(out, "intervention_history.csv")).read().strip().splitlines()
+    assert hist == ["20,80,80", "40,80,80"], hist
+    df = pd.read_csv(os.path.join(out, "tracked_activation_stats.csv"))
+    assert sorted(df["global_step"].unique().tolist()) == [10, 20, 30, 40]
+    from safetensors.torch import load_file
+    sd = load_file(os.path.join(out, "final_model", "vae", "diffusion_pytorch_model.safetensors"))
+    for n in PLANTED:
+        g = sd[n + ".weight"].float()[::8]
+        assert float(g.min()) > 1.0e-3 * 1.05 * 1.05 * 0.5 and float(g.max()) < 5e-3, (n, float(g.min()), float(g.max()))
+    record_parity("train.py unchanged on 2 ranks (torchrun + launch.py): experiment_cifar10_test.yaml 48 steps",
+                  {"intervention_history": hist, "tracked_rows": int(len(df))})

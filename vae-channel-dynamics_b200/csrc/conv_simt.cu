@@ -284,20 +284,25 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
   }
 }
 
-// ws [tap][Co][Ci] fp32 (+ bias ws [Co]) -> OIHW dw / db in the parameter dtype
-__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ bias_src,
-                                      void* __restrict__ dw, void* __restrict__ db, int dt, int Co, int Ci, int taps) {
-  int64_t total = (int64_t)Co * Ci * taps;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int t = (int)(i % taps);
-    int64_t r = i / taps;
-    int ci = (int)(r % Ci);
-    int co = (int)(r / Ci);
-    store_param(dw, dt, i, ws[((int64_t)t * Co + co) * Ci + ci]);
+// ws [tap][Co][Ci] fp32 (+ bias) -> OIHW dw / db in the parameter dtype.  One block = one output channel x 64 input
+// channels x all taps, transposed through shared memory: both the [tap][Co][Ci] reads and the [Co][Ci][tap] writes are
+// contiguous runs (the round-1 kernel read with a stride of Co*Ci floats per thread).
+constexpr int kFinCi = 64;
+__global__ void __launch_bounds__(128) wgrad_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ bias_src,
+                                                             void* __restrict__ dw, void* __restrict__ db, int dt, int Co,
+                                                             int Ci, int taps) {
+  __shared__ float tile[16][kFinCi + 1];
+  const int tiles_ci = (Ci + kFinCi - 1) / kFinCi;
+  const int co = blockIdx.x / tiles_ci, ci0 = (blockIdx.x % tiles_ci) * kFinCi;
+  const int nci = min(kFinCi, Ci - ci0);
+  for (int i = threadIdx.x; i < taps * nci; i += blockDim.x) {
+    const int t = i / nci, c = i - t * nci;
+    tile[t][c] = ws[((int64_t)t * Co + co) * Ci + ci0 + c];
   }
-  if (db)
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Co; i += (int64_t)gridDim.x * blockDim.x)
-      store_param(db, dt, i, bias_src[i]);
+  __syncthreads();
+  const int64_t obase = ((int64_t)co * Ci + ci0) * taps;
+  for (int j = threadIdx.x; j < nci * taps; j += blockDim.x) store_param(dw, dt, obase + j, tile[j % taps][j / taps]);
+  if (db && ci0 == 0 && threadIdx.x == 0) store_param(db, dt, co, bias_src[co]);
 }
 
 Taps make_taps(int KH, int KW, int pad_t, int pad_l, bool dgrad) {
@@ -410,8 +415,12 @@ int conv_bias_grad(const void* dy, float* out, int64_t pixels, int C, cudaStream
 int conv_wgrad_finalize(const float* ws, const float* bias_src, void* dw, void* db, int dtype, int Cout, int Cin, int taps,
                         cudaStream_t st) {
   int64_t total = (int64_t)Cout * Cin * taps;
-  wgrad_finalize_kernel<<<grid_for(total, 256), 256, 0, st>>>(ws, bias_src ? bias_src : ws + total, dw, db, dtype, Cout, Cin,
-                                                             taps);
+  if (taps > 16) {
+    vcd_set_error("conv_wgrad_finalize: at most 16 taps (got %d)", taps);
+    return -1;
+  }
+  const int64_t blocks = (int64_t)Cout * ((Cin + kFinCi - 1) / kFinCi);
+  wgrad_finalize_kernel<<<(unsigned)blocks, 128, 0, st>>>(ws, bias_src ? bias_src : ws + total, dw, db, dtype, Cout, Cin, taps);
   VCD_LAUNCH_CHECK();
   return 0;
 }

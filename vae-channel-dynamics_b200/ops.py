@@ -278,11 +278,12 @@ def pop_gn_sums(t: torch.Tensor, groups: int):
 # SMs the first one's tail leaves idle (wave quantisation: 512->512 at 64^2 has 256 tiles for 74 clusters = 3.46 waves).
 # Measured on B200 (bench.py, 512^2 B=8): 88.77 -> 88.16 ms per step.
 _WGRAD_STREAMS = {}
+wgrad_side_stream_enabled = True      # bench.py switches it off while it times every call with CUDA events
 
 
 def _wgrad_side_stream(device):
     import os
-    if os.environ.get("VCD_WGRAD_STREAM", "1") != "1":
+    if not wgrad_side_stream_enabled or os.environ.get("VCD_WGRAD_STREAM", "1") != "1":
         return None
     st = _WGRAD_STREAMS.get(device)
     if st is None:
@@ -333,11 +334,15 @@ class _ConvFn(torch.autograd.Function):
         dx = dw = db = None
         need_w = ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2])
         side = _wgrad_side_stream(dy.device) if (need_w and ctx.needs_input_grad[0]) else None
+        keep = None
         if side is not None:      # fork: the weight gradient runs concurrently with the data gradient below
             main = torch.cuda.current_stream(dy.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                dw, db = _ConvFn._wgrad(ctx, xs, dy, weight, bias)
+                # `keep`: tensors allocated on the MAIN stream that the side-stream kernels read (the bias-gradient column
+                # sums).  They must stay referenced until the join below is enqueued — freed earlier, the caching allocator
+                # would hand their memory to the main-stream allocations of this very backward (dx, dsdb), racing the read.
+                dw, db, keep = _ConvFn._wgrad(ctx, xs, dy, weight, bias)
         if ctx.needs_input_grad[0]:
             if ctx.gn_info is not None:
                 gx, gsums, ggamma, gbeta, geps, gact, ggroups = ctx.gn_info
@@ -356,7 +361,8 @@ class _ConvFn(torch.autograd.Function):
         if side is not None:      # join: everything after this backward node is ordered after the weight gradient
             torch.cuda.current_stream(dy.device).wait_stream(side)
         elif need_w:
-            dw, db = _ConvFn._wgrad(ctx, xs, dy, weight, bias)
+            dw, db, _ = _ConvFn._wgrad(ctx, xs, dy, weight, bias)
+        del keep
         dres = dy if ctx.has_res and ctx.needs_input_grad[3] else None
         return dx, dw, db, dres, None, None, None, None, None, None, None
 
@@ -370,7 +376,7 @@ class _ConvFn(torch.autograd.Function):
         colsum = pop_colsum(dy) if db is not None else None
         call("vcd_conv2d_wgrad", _p(xs), _p(dy), _p(dw), _p(db), _p(colsum), dtype_code(weight), _p(ws), N, H, W, Cin, Cout,
              KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl, _st())
-        return dw, db
+        return dw, db, colsum
 
 
 def conv2d(x, weight, bias, packs, stride=1, pad_t=1, pad_l=1, out_hw=None, residual=None, impl=None, gn_groups=0):
