@@ -176,3 +176,26 @@ def test_deadneuron_reference_known_answers(src):
     assert trk.percent_history["gn1.bias"] == [(0, 0.0), (20, 0.0)]
     assert set(trk.weights_history) == {"another_conv.weight", "gn1.weight", "gn1.bias"}
     assert len(trk.percent_history) == 8
+
+
+def test_nudge_with_repeated_indices_compounds_like_the_reference_loop(vcd):
+    """nudger.py:128-143 walks the index list sequentially: a repeated index is nudged (and rounded to the parameter dtype,
+    and counted) once per occurrence."""
+    import torch
+    from oracle import components as oc
+    vcd.add_src_to_path()
+    from intervention.nudger import InterventionHandler
+    for dtype in (torch.float32, torch.bfloat16):
+        gn = torch.nn.GroupNorm(32, 64).cuda().to(dtype)
+        with torch.no_grad():
+            gn.weight.copy_(torch.linspace(0.5, 1.4, 64))
+        model = torch.nn.Module()
+        model.norm = gn
+        idx = [3, 5, 3, 3, 63, 64, -1, 5, 60]           # repeats, an out-of-range and a negative index
+        want = gn.weight.detach().cpu().clone()
+        n_want = oc.nudge_gamma(want, idx, 1.2, 1.5)
+        ih = InterventionHandler(model, {"enabled": True, "strategy": "gentle_nudge_groupnorm_scale", "nudge_factor": 1.2,
+                                         "max_scale_value": 1.5, "intervention_interval": 1})
+        ih.intervene({"norm.output": {"param_name_scale": "norm.weight", "inactive_channel_indices": idx}}, 1)
+        assert ih.num_nudges_applied == n_want == 7
+        assert torch.equal(gn.weight.detach().cpu(), want), dtype

@@ -381,3 +381,73 @@ def test_model_wide_weight_pack_equals_per_layer_packs(vcd, dtype):
         assert not any(p.valid for _, _, p, _ in plan.layers)
     assert n == 64 + 8           # 64 convs + 8 attention projections
     assert sum(1 for which in ("encoder", "decoder") for _, _, _, m in vae._pack_weights(which).layers if m == 1) == 3
+
+
+def test_tracked_conv2_and_attention_projection_see_the_pre_residual_tensor(vcd, pair):
+    """The reference's hooks on `resnets.X.conv2` and `attentions.0.to_out.0` observe the module's own output — the skip
+    connection is added OUTSIDE those modules.  The drop-in normally fuses the residual into the GEMM epilogue, so a
+    statistics slot (ActivityMonitor) or a foreign hook on them must switch to the unfused path.  Against oracle hooks."""
+    from oracle.torch_vae import oracle_forward
+    from oracle import components as oc
+    import numpy as np
+    oracle, _ = pair
+    vcd.add_src_to_path()
+    from models.sdxl_vae_wrapper import SDXLVAEWrapper
+    from tracking.monitor import ActivityMonitor
+    w = SDXLVAEWrapper("random-init:42").cuda()
+    w.vae.load_state_dict(oracle.state_dict())
+    names = ["encoder.down_blocks.0.resnets.0.conv2", "encoder.mid_block.attentions.0.to_out.0", "encoder.down_blocks.1.resnets.0.conv1"]
+    mon = ActivityMonitor(w, {"enabled": True, "track_interval": 1, "target_layers": [
+        {"name": "vae." + n, "capture_point": "output", "metrics": ["mean_abs_activation_per_channel"]} for n in names]})
+    ref = {}
+
+    def hook(n):
+        def f(m, i, o):
+            # the reference's metric reduces over every dim but 1 (monitor.py:64-67): per channel for conv outputs
+            # [B, C, H, W], per TOKEN for the Linear output [B, T, C] — the drop-in reports the same vector
+            ref[n] = oc.mean_abs_per_channel(o)
+        return f
+    hs = [oracle.get_submodule(n).register_forward_hook(hook(n)) for n in names]
+    torch.manual_seed(4)
+    x = torch.rand(2, 3, 64, 64, device="cuda") * 2 - 1
+    with torch.no_grad():
+        w(x, sample_posterior=False)
+        oracle_forward(oracle, x, False)
+    [h.remove() for h in hs]
+    mon.step(1)
+    data = mon.get_data_for_step(1)
+    for n in names:
+        got = data["vae." + n + ".output"]["mean_abs_activation_per_channel"]
+        want = ref[n]
+        assert got.shape == want.shape, (n, got.shape, want.shape)
+        err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3)))
+        assert err < 2e-2, (n, err)      # with the residual included the conv2 / to_out.0 statistics would be off by 30-100 %
+    mon.remove_hooks()
+
+
+def test_graphed_step_survives_zero_grad_set_to_none(vcd, pair):
+    """train.py:304 calls optimizer.zero_grad(set_to_none=True) every step: GraphedVAEStep re-attaches the flat-buffer views
+    before every replay, so the optimizer keeps seeing gradients, and a subscribed monitor does not count the warm-up /
+    capture forwards."""
+    oracle, _ = pair
+    vcd.add_src_to_path()
+    from models.sdxl_vae_wrapper import SDXLVAEWrapper
+    from tracking.monitor import ActivityMonitor
+    w = SDXLVAEWrapper("random-init:42", torch_dtype=torch.bfloat16).cuda()
+    mon = ActivityMonitor(w, {"enabled": True, "track_interval": 1, "target_layers": [
+        {"name": "vae.encoder.down_blocks.0.resnets.0.norm1", "capture_point": "output", "metrics": ["mean_abs_activation_per_channel"]}]})
+    x = torch.rand(2, 3, 64, 64, device="cuda") * 2 - 1
+    g = vcd.GraphedVAEStep(w, 1e-6, x)
+    slot = w.vae.encoder.down_blocks[0].resnets[0].norm1._track_out
+    assert float(slot.scal[2]) == 0.0                      # capture / warm-up forwards are not counted
+    opt = torch.optim.AdamW(w.parameters(), lr=1e-3)
+    before = w.vae.decoder.conv_out.weight.detach().clone()
+    for _ in range(2):
+        g.step(x)
+        assert all(p.grad is not None for p in w.parameters())
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        assert all(p.grad is None for p in w.parameters())
+    assert not torch.equal(before, w.vae.decoder.conv_out.weight.detach())
+    assert float(slot.scal[2]) == 2.0
+    mon.remove_hooks()
