@@ -16,7 +16,6 @@ def test_launcher_resolves_dropin_modules_first(tmp_path):
     ref = rh.reference_dir()
     if ref is None:
         pytest.skip("baseline/_ref is missing: run __graft_entry__.build() where /root/reference exists")
-    probe = os.path.join(ref, "src", "_vcd_probe_tmp.py")
     script = tmp_path / "src"
     script.mkdir()
     # a stand-in for train.py living next to a copy of the reference's utils package

@@ -15,6 +15,7 @@ GroupNorm+SiLU / conv+residual kernels instead.
 from __future__ import annotations
 
 import json
+import logging
 import os
 from types import SimpleNamespace
 from typing import Optional
@@ -109,8 +110,9 @@ class B200GroupNorm(nn.GroupNorm):
         if pend is not None:
             if pend[1] == xp.data_ptr():          # the producing conv's output really is this input tensor
                 extra = pend[0]
-            else:                                  # cannot happen through this module tree: never lose statistics silently
-                raise VcdError("statistics hand-off: the tracked conv output is not the input of its GroupNorm")
+            else:   # cannot happen through this module tree; the reference's convention is log + skip, never raise into the loop
+                logging.getLogger(__name__).error("statistics hand-off: the tracked conv output is not the input of its GroupNorm; "
+                                                  "this forward's statistics of that target are dropped")
         y = ops.group_norm(xp, self.weight, self.bias, self.num_groups, self.eps, act,
                            self._track_in, self._track_out, split, feeds_conv_only, slot_in_extra=extra)
         if split:   # (normalised, input routed through for the block's skip connection)
