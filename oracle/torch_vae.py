@@ -10,7 +10,12 @@ unpinned pip dependency of the reference (requirements.txt:8) and is absent from
 this image, and the reference holds no golden tensors for the VAE arithmetic
 (SURVEY.md section 8c).  What pins this file: the module tree must reproduce the
 published SDXL-VAE size (83 653 863 parameters in 248 tensors, checked in
-tests/test_oracle.py) and the call sites below.
+tests/test_oracle.py) and the call sites below; and — an independent implementation
+that IS installed — HF transformers' port of the latent-diffusion autoencoder the
+SDXL-VAE was trained with and diffusers' AutoencoderKL was ported from
+(JanusVQVAEEncoder / JanusVQVAEDecoder, configured with the SDXL-VAE hyper-parameters):
+with this file's weights copied in by name, encoder and decoder outputs agree to
+1e-5 (tests/test_oracle_crosscheck.py).
 
 Reference call sites restated here:
   * src/models/sdxl_vae_wrapper.py:60   vae.encode(x).latent_dist
