@@ -16,6 +16,8 @@ ap.add_argument("--iters", type=int, default=6)
 ap.add_argument("--shapes", nargs="*", default=["128,128,512", "256,256,256", "512,512,128", "512,512,64", "256,128,512",
                                                  "512,256,256"])
 ap.add_argument("--k", type=int, default=3)
+ap.add_argument("--gn-sums", action="store_true", help="fprop also emits the GroupNorm sums of its output from the epilogue "
+                "(as every conv that feeds a GroupNorm does in the model)")
 a = ap.parse_args()
 lib = vcd_b200._lib.lib()
 B, k = a.batch, a.k
@@ -36,9 +38,11 @@ for sh in a.shapes:
     ws = torch.empty(lib.vcd_conv2d_wgrad_ws_bytes(B, h, h, ci, co, k, k, 1) // 4, dtype=torch.float32, device="cuda")
     colsum = torch.zeros(co, dtype=torch.float32, device="cuda")
 
+    osums = torch.empty(B * 32 * 2, dtype=torch.float64, device="cuda") if a.gn_sums else None
+
     def fprop(i):
         call("vcd_conv2d_fprop", _p(xs[i % nbuf]), _p(wf), _p(b32), None, _p(y), None, B, h, h, ci, co, k, k, 1, pad, pad, h, h,
-             0, 0, None, 0, _st())
+             0, 0, _p(osums), 32 if a.gn_sums else 0, _st())
 
     def dgrad(i):
         call("vcd_conv2d_dgrad", _p(gs[i % nbuf]), _p(wf), _p(wd), _p(dx), None, B, h, h, ci, co, k, k, 1, pad, pad, h, h, 0, 0,

@@ -124,7 +124,15 @@ int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, 
   p.Nout = Nout;
   CUtensorMap mA, mB;
   int rc;
-  if ((rc = attach_gn(p, gn, N, Nout, 0, st))) return rc;
+  // 128 -> 128 channel 3x3 layers (N = 128 tile, K = 1152): the item's MMAs last ~4.6k cycles and the GroupNorm-sum epilogue
+  // (32 adds + 32 FMAs + a 15-shuffle transpose-reduce + fp64 atomics per 32-column chunk) does not fit behind them: measured
+  // on B200, 128->128 @512^2 B=8: 0.410 ms without the sums, 0.559 ms with them, against 0.101 ms for the stand-alone
+  // vcd_gn_stats pass over the output (5.3 TB/s).  For these layers the caller's fallback (vcd_gn_stats after the GEMM) wins;
+  // VCD_GN_FUSE_128=1 restores the fused form (A/B measurement).
+  static int fuse128 = -1;
+  if (fuse128 < 0) { const char* e = getenv("VCD_GN_FUSE_128"); fuse128 = (e && e[0] == '1') ? 1 : 0; }
+  const bool short_item = bn == 128 && ntaps * C <= 1152;
+  if ((!short_item || fuse128) && (rc = attach_gn(p, gn, N, Nout, 0, st))) return rc;
   if (gnb) {
     VCD_CHECK_ARG(Nout <= 512 && Nout % 32 == 0, "fused GroupNorm backward: channels must be a multiple of 32, <= 512");
     p.gnb_x = (const bf16*)gnb->x; p.gnb_ab = gnb->ab; p.gnb_dsdb = gnb->dsdb; p.gnb_act = gnb->act;
@@ -936,8 +944,10 @@ extern "C" int vcd_conv2d_dgrad_gn_supported(int N, int H, int W, int Cin, int C
   // 1152) the GEMM item is too short to hide the ~900-instruction fused epilogue — measured on B200: 128->128 @512^2
   // +348 us on the dgrad against 210 us for the stand-alone vcd_gn_bwd_reduce; 256->128 +700 us against 410 us
   // (tools/prof_conv2.py)
+  static int min_c = -1;   // experiment knob: VCD_GNB_MIN_C=128 also fuses the 128-channel layers
+  if (min_c < 0) { const char* e = getenv("VCD_GNB_MIN_C"); min_c = e ? atoi(e) : 256; }
   return (pair_enabled() && umma_shape_ok(Cin, Cout, KH, KW, stride) && KH == 3 && KW == 3 && stride == 1 && W >= 8 &&
-          H >= 16 && Cin <= 512 && Cin >= 256 && Cout >= 256 && Cin % 32 == 0) ? 1 : 0;
+          H >= 16 && Cin <= 512 && Cin >= min_c && Cout >= min_c && Cin % 32 == 0) ? 1 : 0;
 }
 extern "C" int vcd_conv2d_dgrad_gn(const void* dy, const void* w_dgrad, void* g_out, int N, int H, int W, int Cin, int Cout,
                                    int KH, int KW, int pad_t, int pad_l, const void* gn_x, const double* gn_sums,

@@ -505,7 +505,7 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty(acc) & kPeerBitMask);
+      if (lane == 0) mbar_arrive_cluster_relaxed(tempty(acc) & kPeerBitMask);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (GNB && cur_n >= 0) flush_chan_acc();
@@ -689,7 +689,7 @@ umma_pair_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty(acc) & kPeerBitMask);
+      if (lane == 0) mbar_arrive_cluster_relaxed(tempty(acc) & kPeerBitMask);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
