@@ -283,7 +283,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) { if (p.release_arrive) mbar_arrive(tempty_bar(acc)); else mbar_arrive_relaxed(tempty_bar(acc)); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -351,7 +351,11 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int P, i
   return 0;
 }
 
-int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p, int block_n, cudaStream_t st) {
+int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p_in, int block_n, cudaStream_t st) {
+  UmmaParams p = p_in;
+  static int rel = -1;
+  if (rel < 0) { const char* e = getenv("VCD_GEMM_RELEASE"); rel = (e && e[0] == '1') ? 1 : 0; }
+  p.release_arrive = rel;
   int grid = p.total_tiles < vcd_num_sms() ? p.total_tiles : vcd_num_sms();
   if (grid <= 0) return 0;
   if (block_n == 256) {

@@ -56,6 +56,7 @@ struct UmmaParams {
   uint32_t a_kstep, b_kstep;       // descriptor start-address advance (>>4) per K=16 MMA
   uint32_t idesc;
   int total_tiles;
+  int release_arrive;  // A/B knob (VCD_GEMM_RELEASE=1): hand accumulator stages back with a releasing arrive
 };
 
 int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p, int block_n, cudaStream_t st);

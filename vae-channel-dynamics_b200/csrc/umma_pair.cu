@@ -505,7 +505,10 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(tempty(acc) & kPeerBitMask);
+      if (lane == 0) {
+        if (p.release_arrive) mbar_arrive_cluster(tempty(acc) & kPeerBitMask);
+        else mbar_arrive_cluster_relaxed(tempty(acc) & kPeerBitMask);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (GNB && cur_n >= 0) flush_chan_acc();
@@ -809,6 +812,9 @@ int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p,
   if (p.total_items <= 0) return 0;
   ++g_pair_launches;
   {
+    static int rel = -1;
+    if (rel < 0) { const char* e = getenv("VCD_PAIR_RELEASE"); rel = (e && e[0] == '1') ? 1 : 0; }
+    p.release_arrive = rel;
 #ifdef VCD_PAIR_DEBUG
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("VCD_PAIR_DBG"); dbg = e ? atoi(e) : 0; }
