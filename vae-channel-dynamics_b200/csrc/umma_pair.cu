@@ -360,6 +360,23 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       };
       side_load(chalf * (BLOCK_N / 64), sb[0]);
+      // ... and the side input of the NEXT item of this cluster is pulled into L2 now (one prefetch per 128-byte line of this
+      // warp's half of the thread's pixel row): its loads, issued a whole item later, then see L2 latency instead of HBM
+      // latency (ncu source page: the unpack of the side input was the top long-scoreboard stall of the fused kernels)
+      if (side != nullptr && p.side_prefetch && item + n_clusters < p.total_items) {
+        const int item2 = item + n_clusters;
+        const int nt2 = item2 % p.n_tiles;
+        const TileCoord tc2 = decode_tile(p, item2 / p.n_tiles, rank);
+        const int w2 = tc2.w0 + wi, h2 = tc2.h0 + hi;
+        if (tc2.valid && w2 < p.W && h2 < p.H) {
+          const bf16* pf = side + (long long)tc2.n * p.out_sn + (long long)h2 * p.out_sh + (long long)w2 * p.out_sw +
+                           nt2 * BLOCK_N + chalf * (BLOCK_N / 2);
+#pragma unroll
+          for (int l = 0; l < BLOCK_N / 128; ++l)
+            if (nt2 * BLOCK_N + chalf * (BLOCK_N / 2) + l * 64 + 64 <= p.Nout)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + l * 64));
+        }
+      }
       // transposed store (see process_chunk): in store instruction i lane l writes 16 B of row 8i + l/4
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
       long long off_t[4];
@@ -815,6 +832,9 @@ int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p,
     static int rel = -1;
     if (rel < 0) { const char* e = getenv("VCD_PAIR_RELEASE"); rel = (e && e[0] == '1') ? 1 : 0; }
     p.release_arrive = rel;
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("VCD_PAIR_PREFETCH"); pf = (e && e[0] == '0') ? 0 : 1; }
+    p.side_prefetch = pf;
 #ifdef VCD_PAIR_DEBUG
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("VCD_PAIR_DBG"); dbg = e ? atoi(e) : 0; }

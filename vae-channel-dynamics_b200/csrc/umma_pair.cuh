@@ -60,6 +60,7 @@ struct PairParams {
   const float* gnb_ab;     // [N][C][2]: a = gamma * rstd, b = beta - mean * a
   float* gnb_dsdb;         // [N][C][2] fp32, zeroed by the launcher
   int gnb_act;             // 1: SiLU follows the GroupNorm
+  int side_prefetch;   // 1 (default): L2-prefetch the next item's epilogue side input (VCD_PAIR_PREFETCH=0 disables)
   int release_arrive;  // A/B knob (VCD_PAIR_RELEASE=1): epilogue hands accumulator stages back with a RELEASING arrive
   int dbg;  // profiling aid (VCD_PAIR_DBG): 1 = epilogue only hand-shakes, 2 = MMA warp issues no MMAs, 4 = no stores
 };
