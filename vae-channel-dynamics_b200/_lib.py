@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvcd_b200.so")
+# VCD_LIB_PATH: load another build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("VCD_LIB_PATH") or os.path.join(_HERE, "libvcd_b200.so")
 
 F32, BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2

@@ -36,10 +36,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the warp may sleep in hardware up to `ns` nanoseconds.  Without the hint a waiting
+// role warp re-issues the try_wait every ~70 cycles (ncu source page: 10 M loop iterations in a 0.4 ms wgrad kernel).
+// Measured on B200 (same box, bench.py): a 20 us hint changes nothing per kernel and costs 0.3-0.6 ms per step, so the
+// default build does NOT use it (-DVCD_WAIT_HINT_NS=20000 enables it).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+#ifndef VCD_WAIT_HINT_NS
+#define VCD_WAIT_HINT_NS 0
+#endif
+  while (!(VCD_WAIT_HINT_NS ? mbar_try_wait_hint(bar, parity, VCD_WAIT_HINT_NS) : mbar_try_wait(bar, parity))) {
     if (clock64() - t0 > kSpinLimit) {
       printf("vcd umma_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              bar, parity);
