@@ -16,6 +16,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
+// cp.async staging depth (stages of 2 pixels): bytes in flight per thread = stages x 2 x streams x 16
+constexpr int kApplyStages = 4, kReduceStages = 3, kApplyBwdStages = 3, kApplyBwdStagesRes = 2;
 
 struct Map {
   int V, PL, v, pl, c0;
@@ -72,6 +74,83 @@ __device__ __forceinline__ void load_group_stats(const double* sums, int n, int 
   __syncthreads();
 }
 constexpr int kMaxGroups = 64;
+
+// ---------------------------------------------------------------- cp.async staging
+// ncu's source page on the register-staged kernels: 55-70 % of all warp-stall samples sit on the first use of a loaded
+// vector (long scoreboard) with the issue slots 34-54 % busy and DRAM at 67-76 % — latency-bound on bytes in flight, and
+// the registers (80 per thread for 3 resident blocks) allow only 64-96 bytes per thread.  cp.async (LDGSTS) keeps the loads
+// out of the register file: every thread streams its 16-byte vectors of NS tensors through its OWN shared-memory slots,
+// ST stages of U pixels deep (2-3x the bytes in flight), and reads a slot back only after cp.async.wait_group has retired
+// the group that filled it — no block-level synchronisation, each thread only ever reads what it requested itself.
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int NS, int U, int ST>
+struct Pipe {
+  static constexpr int kBytes = ST * U * NS * kThreads * 16;
+  uint32_t base;
+  __device__ __forceinline__ explicit Pipe(void* smem) : base(gn_smem_u32(smem) + threadIdx.x * 16u) {}
+  __device__ __forceinline__ uint32_t slot(int st, int u, int s) const {
+    return base + (uint32_t)(((st * U + u) * NS + s) * kThreads) * 16u;
+  }
+  __device__ __forceinline__ void issue(int st, int u, int s, const void* g) const {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot(st, u, s)), "l"(g) : "memory");
+  }
+  __device__ __forceinline__ void commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void wait_oldest() const { asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory"); }
+  __device__ __forceinline__ void drain() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  __device__ __forceinline__ bf16x8 read(int st, int u, int s) const {
+    bf16x8 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.u.x), "=r"(v.u.y), "=r"(v.u.z), "=r"(v.u.w)
+                 : "r"(slot(st, u, s))
+                 : "memory");
+    return v;
+  }
+};
+// Walks the thread's pixels (m.p_begin + m.pl, step m.PL) through the pipe.  `src(s)` = base pointer of stream s (already
+// offset to the thread's channels), `body(p, v)` consumes the NS vectors of pixel p.
+template <int NS, int U, int ST, typename Src, typename Body>
+__device__ __forceinline__ void stream_pixels(void* smem, const Map& m, int C, Src src, Body body) {
+  Pipe<NS, U, ST> pipe(smem);
+  const int64_t stride = (int64_t)m.PL;
+  int64_t pq = m.p_begin + m.pl;          // next pixel to request
+#pragma unroll
+  for (int st = 0; st < ST; ++st) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pq < m.p_end) {
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) pipe.issue(st, u, s2, src(s2) + pq * C);
+      }
+      pq += stride;
+    }
+    pipe.commit();
+  }
+  int st = 0;
+  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * stride) {
+    pipe.wait_oldest();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + (int64_t)u * stride;
+      if (p < m.p_end) {
+        bf16x8 v[NS];
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) v[s2] = pipe.read(st, u, s2);
+        body(p, v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {          // refill the stage just consumed
+      if (pq < m.p_end) {
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2) pipe.issue(st, u, s2, src(s2) + pq * C);
+      }
+      pq += stride;
+    }
+    pipe.commit();
+    st = (st + 1 == ST) ? 0 : st + 1;
+  }
+  pipe.drain();
+}
 
 // All hot loops below use packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, common.cuh): a thread's 8 channels are 4 pairs.
 // SiLU and its derivative go through ONE tanh per element on the half-argument u = y/2 (constants pre-halved):
@@ -144,30 +223,20 @@ __global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) gn_stats_kernel(const
   Stat5 st;
   st.init();
   const bf16* xb = x + (int64_t)n * HW * C + m.c0;
-  constexpr int U = STATS ? 6 : kUnroll;   // 2 resident blocks with statistics: 6 x 16 B in flight per thread
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
-    bf16x8 v[U];
+  stream_pixels<1, 2, kApplyStages>(red, m, C, [&](int) { return xb; }, [&](int64_t, const bf16x8* v) {
+    f32x2 f[4];
+    unpack8x(v[0], f);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p < m.p_end) v[u] = ld8(xb + p * C);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (p0 + (int64_t)u * m.PL >= m.p_end) break;
-      f32x2 f[4];
-      unpack8x(v[u], f);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (STATS) {
-          st.add<NZ>(j, f[j], near_zero);
-        } else {
-          st.s[j] = add2(st.s[j], f[j]);
-          st.q[j] = fma2(f[j], f[j], st.q[j]);
-        }
+    for (int j = 0; j < 4; ++j) {
+      if (STATS) {
+        st.add<NZ>(j, f[j], near_zero);
+      } else {
+        st.s[j] = add2(st.s[j], f[j]);
+        st.q[j] = fma2(f[j], f[j], st.q[j]);
       }
     }
-  }
+  });
+  __syncthreads();   // the reduction below reuses the staging memory
   float acc[5][8];
   st.to_acc(acc);
   deposit<K>(red, m, acc);
@@ -228,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, (SIN || SOUT) ? 2 : 3) gn_apply_kern
                                                                int pdt, bf16* __restrict__ out, float* __restrict__ cstats_in,
                                                                float* __restrict__ cstats_out, float near_zero, float eps,
                                                                int HW, int C, int G, int ppb) {
-  extern __shared__ float sm[];  // [5][8][PL][V] when SIN || SOUT
+  extern __shared__ float sm[];  // cp.async staging, then [5][8][PL][V] for the statistics reduction
   const int n = blockIdx.y;
   Map m = make_map(C, HW, ppb);
   const int D = C / G;
@@ -241,34 +310,22 @@ __global__ void __launch_bounds__(kThreads, (SIN || SOUT) ? 2 : 3) gn_apply_kern
   if (SIN) sin.init();
   if (SOUT) sout.init();
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  // bytes in flight per SM: 3 blocks x 256 threads x 4 x 16 B = 48 KB without statistics; the statistics variants hold 40-80
-  // accumulator registers, run 2 blocks per SM and keep 6 (4 with both slots) loads in flight per thread instead
-  constexpr int U = (SIN || SOUT) ? 6 : kUnroll;
   float npix = 0.f;   // pixels this thread processed (SIN && SOUT: output sums are derived from the input sums)
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
-    bf16x8 v[U];
+  const bf16* xb = x + base;
+  stream_pixels<1, 2, kApplyStages>(sm, m, C, [&](int) { return xb; }, [&](int64_t p, const bf16x8* v) {
+    f32x2 f[4];
+    unpack8x(v[0], f);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p < m.p_end) v[u] = ld8(x + base + p * C);
+    for (int j = 0; j < 4; ++j) {
+      if (SIN) sin.add<NZ>(j, f[j], near_zero);
+      const f32x2 w = fma2(ka[j], f[j], kb[j]);       // ACT: u = y/2, else y
+      if (SOUT) sout.add<NZ, SIN && SOUT>(j, ACT ? add2(w, w) : w, near_zero);
+      f[j] = ACT ? fma2(w, tanh2(w), w) : w;           // silu(y) = u + u*tanh(u)
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p >= m.p_end) break;
-      f32x2 f[4];
-      unpack8x(v[u], f);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (SIN) sin.add<NZ>(j, f[j], near_zero);
-        const f32x2 w = fma2(ka[j], f[j], kb[j]);       // ACT: u = y/2, else y
-        if (SOUT) sout.add<NZ, SIN && SOUT>(j, ACT ? add2(w, w) : w, near_zero);
-        f[j] = ACT ? fma2(w, tanh2(w), w) : w;           // silu(y) = u + u*tanh(u)
-      }
-      st8(out + base + p * C, pack8x(f));
-      if (SIN && SOUT) npix += 1.f;
-    }
-  }
+    st8(out + base + p * C, pack8x(f));
+    if (SIN && SOUT) npix += 1.f;
+  });
+  if (SIN || SOUT) __syncthreads();   // the statistics reduction below reuses the staging memory
   if (SIN && SOUT) {
     const f32x2 two = dup2(ACT ? 2.f : 1.f), n2 = dup2(npix);
 #pragma unroll
@@ -312,31 +369,19 @@ __global__ void __launch_bounds__(kThreads, 3) gn_bwd_reduce_kernel(const bf16* 
 #pragma unroll
   for (int j = 0; j < 4; ++j) ds[j] = db[j] = 0ull;
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  constexpr int U = 2;
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
-    bf16x8 vx[U], vg[U];
+  const bf16 *xb = x + base, *gb = dout + base;
+  stream_pixels<2, 2, kReduceStages>(sm, m, C, [&](int s2) { return s2 == 0 ? xb : gb; }, [&](int64_t, const bf16x8* v) {
+    f32x2 f[4], g[4];
+    unpack8x(v[0], f);
+    unpack8x(v[1], g);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p < m.p_end) {
-        vx[u] = ld8(x + base + p * C);
-        vg[u] = ld8(dout + base + p * C);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const f32x2 gg = ACT ? silu_grad_times(g[j], fma2(ka[j], f[j], kb[j])) : g[j];
+      ds[j] = fma2(gg, f[j], ds[j]);
+      db[j] = add2(db[j], gg);
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (p0 + (int64_t)u * m.PL >= m.p_end) break;
-      f32x2 f[4], g[4];
-      unpack8x(vx[u], f);
-      unpack8x(vg[u], g);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const f32x2 gg = ACT ? silu_grad_times(g[j], fma2(ka[j], f[j], kb[j])) : g[j];
-        ds[j] = fma2(gg, f[j], ds[j]);
-        db[j] = add2(db[j], gg);
-      }
-    }
-  }
+  });
+  __syncthreads();   // the reduction below reuses the staging memory
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -407,47 +452,34 @@ __global__ void __launch_bounds__(kThreads, 3) gn_bwd_apply_kernel(const bf16* _
     }
   }
   const int64_t base = (int64_t)n * HW * C + m.c0;
-  constexpr int U = 2;
-  for (int64_t p0 = m.p_begin + m.pl; p0 < m.p_end; p0 += (int64_t)U * m.PL) {
-    bf16x8 vx[U], vg[U], vr[U];
+  const bf16 *xb = x + base, *gb = dout + base, *rb = HAS_RES ? dres + base : nullptr;
+  stream_pixels<HAS_RES ? 3 : 2, 2, HAS_RES ? kApplyBwdStagesRes : kApplyBwdStages>(
+      sm, m, C, [&](int s2) { return s2 == 0 ? xb : (s2 == 1 ? gb : rb); }, [&](int64_t p, const bf16x8* v) {
+        f32x2 f[4], g[4], r[4];
+        unpack8x(v[0], f);
+        unpack8x(v[1], g);
+        if (HAS_RES) unpack8x(v[HAS_RES ? 2 : 1], r);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p < m.p_end) {
-        vx[u] = ld8(x + base + p * C);
-        vg[u] = ld8(dout + base + p * C);
-        if (HAS_RES) vr[u] = ld8(dres + base + p * C);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t p = p0 + (int64_t)u * m.PL;
-      if (p >= m.p_end) break;
-      f32x2 f[4], g[4], r[4];
-      unpack8x(vx[u], f);
-      unpack8x(vg[u], g);
-      if (HAS_RES) unpack8x(vr[u], r);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f32x2 e = fma2(c2[WIDE ? (j >> 1) * 2 : j], f[j], c3[WIDE ? (j >> 1) * 2 : j]);
-        if (HAS_RES) e = add2(e, r[j]);
-        f32x2 d;
-        if (ACT) {
-          const f32x2 uu = fma2(ka[j], f[j], kb[j]);
-          const f32x2 t = tanh2(uu);
-          const f32x2 v = fma2(neg2(t), t, dup2(1.f));
-          const f32x2 rr = fma2(uu, v, t);
-          const f32x2 k = mul2(ka[j], g[j]);
-          d = fma2(k, rr, add2(e, k));
-        } else {
-          d = fma2(ka[j], g[j], e);
+        for (int j = 0; j < 4; ++j) {
+          f32x2 e = fma2(c2[WIDE ? (j >> 1) * 2 : j], f[j], c3[WIDE ? (j >> 1) * 2 : j]);
+          if (HAS_RES) e = add2(e, r[j]);
+          f32x2 d;
+          if (ACT) {
+            const f32x2 uu = fma2(ka[j], f[j], kb[j]);
+            const f32x2 t = tanh2(uu);
+            const f32x2 vv = fma2(neg2(t), t, dup2(1.f));
+            const f32x2 rr = fma2(uu, vv, t);
+            const f32x2 k = mul2(ka[j], g[j]);
+            d = fma2(k, rr, add2(e, k));
+          } else {
+            d = fma2(ka[j], g[j], e);
+          }
+          cs[j] = add2(cs[j], d);
+          g[j] = d;
         }
-        cs[j] = add2(cs[j], d);
-        g[j] = d;
-      }
-      st8(dx + base + p * C, pack8x(g));
-    }
-  }
+        st8(dx + base + p * C, pack8x(g));
+      });
+  if (colsum) __syncthreads();   // the column-sum reduction below reuses the staging memory
   if (colsum) {
     float acc[1][8];
 #pragma unroll
@@ -562,6 +594,11 @@ int gn_make_ab(const double* sums, const void* gamma, const void* beta, int pdt,
   return 0;
 }
 
+static size_t stats_smem(int K, int C) {   // cp.async staging, reused for the [K][8][kThreads] + [C][2] floats of the reduction
+  const size_t red = (size_t)(K * 8 * kThreads + 2 * C) * sizeof(float), pipe = Pipe<1, 2, kApplyStages>::kBytes;
+  return red > pipe ? red : pipe;
+}
+
 extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, float near_zero, int N, int HW, int C,
                             int G, vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
@@ -569,13 +606,13 @@ extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, f
   VCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * G, st));
   const GnShape sh = gn_launch_shape(N, HW, C, chan_stats_in ? 2 : 3);
   if (chan_stats_in && near_zero > 0.f)
-    gn_stats_kernel<true, true><<<sh.grid, kThreads, (5 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
+    gn_stats_kernel<true, true><<<sh.grid, kThreads, stats_smem(5, C), st>>>(
         (const bf16*)x, sums, chan_stats_in, near_zero, HW, C, G, sh.ppb);
   else if (chan_stats_in)
-    gn_stats_kernel<true, false><<<sh.grid, kThreads, (5 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
+    gn_stats_kernel<true, false><<<sh.grid, kThreads, stats_smem(5, C), st>>>(
         (const bf16*)x, sums, chan_stats_in, near_zero, HW, C, G, sh.ppb);
   else
-    gn_stats_kernel<false, false><<<sh.grid, kThreads, (2 * 8 * kThreads + 2 * C) * sizeof(float), st>>>(
+    gn_stats_kernel<false, false><<<sh.grid, kThreads, stats_smem(2, C), st>>>(
         (const bf16*)x, sums, nullptr, near_zero, HW, C, G, sh.ppb);
   VCD_LAUNCH_CHECK();
   return 0;
@@ -588,7 +625,8 @@ extern "C" int vcd_gn_apply_fwd(const void* x, const double* sums, const void* g
   cudaStream_t st = as_stream(stream);
   const bool sin = chan_stats_in != nullptr, sout = chan_stats_out != nullptr;
   const GnShape sh = gn_launch_shape(N, HW, C, (sin || sout) ? 2 : 3);
-  const size_t smem = (sin || sout) ? 5 * 8 * kThreads * sizeof(float) : 0;
+  size_t smem = Pipe<1, 2, kApplyStages>::kBytes;
+  if ((sin || sout) && smem < 5 * 8 * kThreads * sizeof(float)) smem = 5 * 8 * kThreads * sizeof(float);
 #define VCD_GN_APPLY(ACT, SIN, SOUT)                                                                                    \
   do {                                                                                                                  \
     if ((SIN || SOUT) && near_zero > 0.f)                                                                               \
@@ -623,7 +661,9 @@ extern "C" int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* 
   cudaStream_t st = as_stream(stream);
   VCD_CUDA(cudaMemsetAsync(dsdb, 0, sizeof(float) * 2 * N * C, st));
   const GnShape sh = gn_launch_shape(N, HW, C, 3);
-  const size_t smem = 2 * 8 * kThreads * sizeof(float);
+  const size_t smem = Pipe<2, 2, kReduceStages>::kBytes;   // >= the [2][8][kThreads] floats of the final reduction
+  VCD_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VCD_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (act_silu)
     gn_bwd_reduce_kernel<true><<<sh.grid, kThreads, smem, st>>>((const bf16*)x, (const bf16*)dout, sums, gamma, beta,
                                                                 param_dtype, dsdb, eps, HW, C, G, sh.ppb);
@@ -641,11 +681,13 @@ extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* s
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
   if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
-  const size_t smem = dx_colsum ? 8 * kThreads * sizeof(float) : 0;
+  const size_t smem = dres ? Pipe<3, 2, kApplyBwdStagesRes>::kBytes : Pipe<2, 2, kApplyBwdStages>::kBytes;   // >= 8 * kThreads floats
   const GnShape sh = gn_launch_shape(N, HW, C, 3);
   const bool wide = ((C / G) & 3) == 0;
 #define VCD_GN_BWD(ACT, RES)                                                                                              \
   do {                                                                                                                    \
+    VCD_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<ACT, RES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    VCD_CUDA(cudaFuncSetAttribute(gn_bwd_apply_kernel<ACT, RES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     if (wide)                                                                                                             \
       gn_bwd_apply_kernel<ACT, RES, true><<<sh.grid, kThreads, smem, st>>>(                                               \
           (const bf16*)x, (const bf16*)dout, sums, gamma, beta, param_dtype, dsdb, (bf16*)dx, (const bf16*)dres, dx_colsum, \
