@@ -326,14 +326,22 @@ def conv_roofline(torch, vcd, R, B, peaks):
         else:
             packs = ops.PackedWeights()
             run = lambda i: ops.conv2d(xs[i % nbuf], w, bias, packs, stride=1, pad_t=pad, pad_l=pad).backward(g)
-        for i in range(3):
+        def step(i, run=run, xs=xs, w=w, bias=bias):
+            # as in the training step, no gradient is ACCUMULATED: activations are non-leaf there and zero_grad() sets the
+            # parameter gradients to None, so the kernels' outputs become the gradients without a read-modify-write pass
+            xs[i % nbuf].grad = None
+            w.grad = None
+            bias.grad = None
             run(i)
+
+        for i in range(3):
+            step(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 5
         torch.cuda.synchronize()
         e0.record()
         for i in range(iters):
-            run(i)
+            step(i)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters

@@ -142,3 +142,29 @@ def test_two_rank_ddp_matches_single_process(vcd):
         assert r["classified"] == {TRACK[1] + ".output": 16, TRACK[2] + ".output": 64}, r
         assert r["diverged_before_sync"] and r["equal_after_sync"] and r["nudge_visible"], r
     assert res[0]["nudged"] == 80 and res[1]["nudged"] == 0
+
+
+@pytest.mark.timeout(600)
+def test_model_on_a_non_current_device(vcd):
+    """One process, two GPUs: the drop-in on cuda:1 while cuda:0 is the current device gives the result of the same model on
+    cuda:0 (encode / decode make the tensor's device current; per-device kernel attributes and SM counts)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import vcd_b200
+    from util import rel_err
+    vcd_b200.add_src_to_path()
+    from models.sdxl_vae_wrapper import SDXLVAEWrapper
+    torch.cuda.set_device(0)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        w = SDXLVAEWrapper("random-init:42").to(dev)
+        out = w(x.to(dev), sample_posterior=False)
+        total, _, _ = vcd_b200.vae_loss(out, x.to(dev), 1e-6)
+        total.backward()
+        assert torch.cuda.current_device() == 0
+        outs.append((out["reconstruction"].detach().float().cpu(), float(total),
+                     w.vae.decoder.conv_in.weight.grad.detach().float().cpu()))
+    assert rel_err(outs[1][0], outs[0][0]) < 2e-2 and abs(outs[1][1] - outs[0][1]) < 1e-2 * abs(outs[0][1])
+    assert rel_err(outs[1][2], outs[0][2]) < 5e-2

@@ -7,6 +7,7 @@ rebuilt on every forward (fused optimizers do not bump ``param._version``, so no
 """
 from __future__ import annotations
 
+import functools
 import math
 from typing import Optional
 
@@ -32,6 +33,22 @@ def _st() -> int:
     # raw cudaStream_t of the current stream of the current device (torch.cuda.current_stream() builds a Stream object and
     # costs ~16 us per call — 6 ms of host time per training step)
     return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+def _on_tensor_device(fwd):
+    """Decorator of every autograd Function.forward below: kernels go to the CURRENT stream of the CURRENT device (_st), so a
+    tensor that lives on another GPU (a model on cuda:1 in a process whose current device is cuda:0) makes its own device
+    current for the call.  Backward nodes already run under autograd's device guard."""
+    @functools.wraps(fwd)
+    def guarded(ctx, *args, **kw):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fwd(ctx, *args, **kw)
+                break
+        return fwd(ctx, *args, **kw)
+    return guarded
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -293,6 +310,7 @@ def _wgrad_side_stream(device):
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, weight, bias, residual, packs: PackedWeights, stride: int, pad_t: int, pad_l: int,
                 out_hw, impl: int, gn_groups: int = 0):
         x = _nhwc(x)
@@ -434,6 +452,7 @@ class _UpConvFn(torch.autograd.Function):
     GEMMs do 16/36 of the multiply-adds."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, weight, bias, packs: UpconvPackedWeights, gn_groups: int = 0):
         x = _nhwc(x)
         N, H, W, Cin = x.shape
@@ -485,6 +504,7 @@ class _GroupNormFn(torch.autograd.Function):
     gradient of the conv that produced x)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, gamma, beta, groups: int, eps: float, act: bool, slot_in: Optional[TrackSlot],
                 slot_out: Optional[TrackSlot], split: bool, sole_consumer_is_conv: bool = False,
                 slot_in_extra: Optional[TrackSlot] = None):
@@ -566,6 +586,7 @@ def group_norm(x, gamma, beta, groups, eps, act, slot_in=None, slot_out=None, sp
 # ------------------------------------------------------------------------------------------
 class _SiluFn(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x):
         x = _nhwc(x)
         y = torch.empty_like(x)
@@ -584,6 +605,7 @@ class _SiluFn(torch.autograd.Function):
 
 class _AddFn(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, a, b):
         a, b = _nhwc(a), _nhwc(b)
         o = torch.empty_like(a)
@@ -597,6 +619,7 @@ class _AddFn(torch.autograd.Function):
 
 class _Upsample2xFn(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x):
         x = _nhwc(x)
         N, H, W, C = x.shape
@@ -618,6 +641,7 @@ class _ToNHWC(torch.autograd.Function):
     """[N, C, H, W] (fp32 | bf16, any strides) -> bf16 NHWC."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x):
         _require_cuda(x, "model input")
         N, C, H, W = x.shape
@@ -643,6 +667,7 @@ class _ToNCHW(torch.autograd.Function):
     """bf16 NHWC -> contiguous [N, C, H, W] in `dtype` (what train.py / evaluate.py consume)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, dtype):
         x = _nhwc(x)
         N, H, W, C = x.shape
@@ -707,6 +732,7 @@ def _transpose(x, batch, rows, cols):
 
 class _AttnCoreFn(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, q, k, v):
         q, k, v = _nhwc(q), _nhwc(k), _nhwc(v)
         N, C = q.shape[0], q.shape[-1]
@@ -757,6 +783,7 @@ class _GaussFn(torch.autograd.Function):
     """moments [N,h,w,8] (+ noise [N,4,h,w] fp32) -> z [N,h,w,4] bf16, kl [N] fp32, mean/logvar [N,4,h,w] fp32."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, moments, noise):
         moments = _nhwc(moments)
         N, h, w, C2 = moments.shape
@@ -795,6 +822,7 @@ class _MseFn(torch.autograd.Function):
     """mean((rec - x)^2) with rec bf16 NHWC and x the fp32 NCHW loader tensor (train.py:289)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, rec, x):
         rec = _nhwc(rec)
         N, H, W, C = rec.shape

@@ -14,6 +14,7 @@ GroupNorm+SiLU / conv+residual kernels instead.
 """
 from __future__ import annotations
 
+import contextlib
 import json
 import logging
 import os
@@ -42,6 +43,11 @@ SDXL_VAE_CONFIG = {
     "force_upcast": True,
 }
 _NORM_EPS = 1e-6
+
+
+def _device_of(t: torch.Tensor):
+    """Context manager that makes `t`'s CUDA device current (a no-op context for CPU tensors, whose first kernel call raises)."""
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
 def _phys(x: torch.Tensor) -> torch.Tensor:
@@ -460,26 +466,30 @@ class B200AutoencoderKL(nn.Module):
             raise VcdError(f"encode expects [N, 3, H, W], got {tuple(x.shape)}")
         self._sync_gamma_if_pending()
         ops.clear_colsums()
-        plan = self._pack_weights("encoder") if x.is_cuda else None
-        try:
-            moments = self.quant_conv(self.encoder(x))
-        finally:
-            if plan is not None:
-                plan.expire()
-        dist = DiagonalGaussianDistribution(moments)
+        # every kernel goes to torch's CURRENT stream of the CURRENT device: make the input's device current for the call
+        # (a model on cuda:1 in a process whose current device is cuda:0; backward nodes run under autograd's own guard)
+        with _device_of(x):
+            plan = self._pack_weights("encoder") if x.is_cuda else None
+            try:
+                moments = self.quant_conv(self.encoder(x))
+            finally:
+                if plan is not None:
+                    plan.expire()
+            dist = DiagonalGaussianDistribution(moments)
         return SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True):
         if not torch.is_grad_enabled():
             ops.clear_colsums()     # decode-only loops (wrapper.decode, logit lens): drop stale producer->consumer hand-offs
-        plan = self._pack_weights("decoder") if z.is_cuda else None
-        try:
-            y = self.decoder(self.post_quant_conv(z))          # logical [N, 3, H, W] bf16
-        finally:
-            if plan is not None:
-                plan.expire()
-        sample = ops.to_nchw(_phys(y), self.output_dtype)  # contiguous NCHW, fp32
-        sample._vcd_nhwc = _phys(y)                        # fused-loss fast path (vcd_b200.losses)
+        with _device_of(z):
+            plan = self._pack_weights("decoder") if z.is_cuda else None
+            try:
+                y = self.decoder(self.post_quant_conv(z))          # logical [N, 3, H, W] bf16
+            finally:
+                if plan is not None:
+                    plan.expire()
+            sample = ops.to_nchw(_phys(y), self.output_dtype)  # contiguous NCHW, fp32
+            sample._vcd_nhwc = _phys(y)                        # fused-loss fast path (vcd_b200.losses)
         return SimpleNamespace(sample=sample) if return_dict else (sample,)
 
     def forward(self, sample, sample_posterior: bool = False, generator=None):
