@@ -106,6 +106,47 @@ def test_forward_backward_matches_oracle(vcd, pair, monkeypatch, impl, R, B):
         vcd.ops.set_conv_impl(vcd._lib.IMPL_AUTO)
 
 
+@pytest.mark.parametrize("H,W,B", [(88, 72, 3), (136, 200, 1), (264, 312, 1)])
+def test_ragged_image_sizes_match_oracle(vcd, pair, monkeypatch, H, W, B):
+    """Sizes that are multiples of 8 only (the three downsamplers) but of none of the kernel tiles: partial 8x16 halo tiles
+    (TMA zero fill, masked stores), an odd number of tiles per image (the second CTA of the last pair idles), levels below the
+    halo kernel's minimum (11 x 9 at 88 x 72), 33 x 39 tokens in the attention block, odd batch.  Forward, losses and all 248
+    gradients against the fp32 oracle at the network-level gates of test_forward_backward_matches_oracle."""
+    from oracle.torch_vae import oracle_forward, oracle_losses
+    oracle, model = pair
+    torch.manual_seed(11)
+    x = torch.rand(B, 3, H, W, device="cuda") * 2 - 1
+    noise = torch.randn(B, 4, H // 8, W // 8, device="cuda")
+    oracle.zero_grad(set_to_none=True)
+    model.zero_grad(set_to_none=True)
+    oo = oracle_forward(oracle, x, True, noise=noise)
+    ot, orec, okl = oracle_losses(oo, x, 1e-6)
+    ot.backward()
+    _patch_noise(monkeypatch, noise)
+    dist = model.encode(x).latent_dist
+    rec = model.decode(dist.sample()).sample
+    assert rec.shape == x.shape and rec.dtype == torch.float32 and rec.is_contiguous()
+    mt, mrec, mkl = vcd.vae_loss({"reconstruction": rec, "latent_dist": dist}, x, 1e-6)
+    mt.backward()
+    og = dict(oracle.named_parameters())
+    # conv biases that feed a GroupNorm have a true gradient of zero (mean-shift invariance): their "relative error" is noise
+    # over noise, so tensors whose fp32 gradient norm is below 1e-4 of the largest are compared absolutely, not relatively
+    big = max(float(p.grad.norm()) for p in og.values())
+    keep = [n for n, p in og.items() if float(p.grad.norm()) > 1e-4 * big]
+    named = dict(model.named_parameters())
+    e = torch.tensor([rel_err(named[n].grad, og[n].grad) for n in keep])
+    for n in og:
+        if n not in keep:
+            assert float(named[n].grad.float().norm()) < 1e-2 * big, n
+    measured = {"latent mean": rel_err(dist.mean, oo["latent_dist"].mean), "reconstruction": rel_err(rec, oo["reconstruction"]),
+                "rec_loss": abs(float(mrec) - float(orec)) / float(orec), "kl": abs(float(mkl) - float(okl)) / float(okl),
+                "grad_median": float(e.median()), "grad_max": float(e.max()), "grad_tensors_compared": len(keep)}
+    record_parity(f"test_model_gpu ragged H={H} W={W} B={B} params=fp32", measured)
+    assert measured["latent mean"] < 2.75e-2 and measured["reconstruction"] < 4.0e-2, measured
+    assert measured["rec_loss"] < 1e-2 and measured["kl"] < 1e-2, measured
+    assert measured["grad_median"] < 3.4e-2 and measured["grad_max"] < 0.2, measured
+
+
 def test_eval_mode_path_and_wrapper(vcd, pair):
     from oracle.torch_vae import oracle_forward
     oracle, model = pair

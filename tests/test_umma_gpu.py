@@ -79,8 +79,10 @@ def test_gemm_tn(vcd, batch, M, N, K, red):
     assert rel_err(D, ref) < TOL
 
 
-@pytest.mark.parametrize("T", [64, 256, 1024])
+@pytest.mark.parametrize("T", [64, 256, 1024, 99, 9, 1287])
 def test_attention_core(vcd, T):
+    """T = 99 (11 x 9), 9 (3 x 3), 1287 (33 x 39): token counts that are no multiple of the 64-wide K step are zero-padded,
+    the padded keys masked with -inf scores"""
     ops = vcd.ops
     N, C = 2, 512
     q, k, v = [bf16_round(torch.randn(N, T, C, device="cuda")) for _ in range(3)]

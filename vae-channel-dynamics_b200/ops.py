@@ -730,45 +730,66 @@ def _transpose(x, batch, rows, cols):
     return y
 
 
+def _pad_tokens(x, N, T, Tp, C):
+    """[N, T, C] -> zero-padded [N, Tp, C] (token counts that are not a multiple of the GEMM K step, e.g. 11 x 9 = 99)."""
+    y = x.new_zeros((N, Tp, C))
+    y[:, :T] = x.reshape(N, T, C)
+    return y
+
+
 class _AttnCoreFn(torch.autograd.Function):
+    """softmax(Q K^T / sqrt(C)) V for ONE head of C channels over T = h*w tokens (diffusers Attention in the VAE mid blocks).
+    T is padded to a multiple of 64 when it is not one (the P.V product contracts over tokens in 64-wide K steps): padded
+    keys get a score of -inf, so their probabilities — and every gradient that flows through them — are exactly zero."""
+
     @staticmethod
     @_on_tensor_device
     def forward(ctx, q, k, v):
         q, k, v = _nhwc(q), _nhwc(k), _nhwc(v)
+        shape = q.shape
         N, C = q.shape[0], q.shape[-1]
         T = q.numel() // (N * C)
+        Tp = (T + 63) // 64 * 64
+        if Tp != T:
+            q, k, v = (_pad_tokens(t, N, T, Tp, C) for t in (q, k, v))
         scale = 1.0 / math.sqrt(C)
         dev = q.device
-        s = torch.empty((N, T, T), dtype=torch.bfloat16, device=dev)
-        _gemm_nt(q, k, s, N, T, T, C, True, alpha=scale)
+        s = torch.empty((N, Tp, Tp), dtype=torch.bfloat16, device=dev)
+        _gemm_nt(q, k, s, N, Tp, Tp, C, True, alpha=scale)
+        if Tp != T:
+            s[:, :, T:] = float("-inf")
         p = torch.empty_like(s)
-        call("vcd_softmax_fwd", _p(s), _p(p), N * T, T, _st())
+        call("vcd_softmax_fwd", _p(s), _p(p), N * Tp, Tp, _st())
         del s
-        vt = _transpose(v, N, T, C)  # [N][C][T]
+        vt = _transpose(v, N, Tp, C)  # [N][C][Tp]
         o = torch.empty_like(q)
-        _gemm_nt(p, vt, o, N, T, C, T, True)
+        _gemm_nt(p, vt, o, N, Tp, C, Tp, True)
         ctx.save_for_backward(q, k, v, p)
-        ctx.meta = (N, T, C, scale)
-        return o
+        ctx.meta = (N, T, Tp, C, scale, shape)
+        return o if Tp == T else o[:, :T].reshape(shape)
 
     @staticmethod
     def backward(ctx, do):
         q, k, v, p = ctx.saved_tensors
-        N, T, C, scale = ctx.meta
+        N, T, Tp, C, scale, shape = ctx.meta
         do = _nhwc(do)
+        if Tp != T:
+            do = _pad_tokens(do, N, T, Tp, C)
         dev = q.device
         dv = torch.empty_like(v)
-        _gemm_tn(p, do, dv, N, T, C, T, False)            # dV[j][c] = sum_i P[i][j] dO[i][c]
-        dp = torch.empty((N, T, T), dtype=torch.bfloat16, device=dev)
-        _gemm_nt(do, v, dp, N, T, T, C, True)              # dP[i][j] = sum_c dO[i][c] V[j][c]
+        _gemm_tn(p, do, dv, N, Tp, C, Tp, False)           # dV[j][c] = sum_i P[i][j] dO[i][c]
+        dp = torch.empty((N, Tp, Tp), dtype=torch.bfloat16, device=dev)
+        _gemm_nt(do, v, dp, N, Tp, Tp, C, True)            # dP[i][j] = sum_c dO[i][c] V[j][c]
         ds = torch.empty_like(dp)
-        call("vcd_softmax_bwd", _p(p), _p(dp), _p(ds), scale, N * T, T, _st())
+        call("vcd_softmax_bwd", _p(p), _p(dp), _p(ds), scale, N * Tp, Tp, _st())
         del dp
-        kt = _transpose(k, N, T, C)                        # [N][C][T]
+        kt = _transpose(k, N, Tp, C)                       # [N][C][Tp]
         dq = torch.empty_like(q)
-        _gemm_nt(ds, kt, dq, N, T, C, T, True)             # dQ[i][c] = sum_j dS[i][j] K[j][c]
+        _gemm_nt(ds, kt, dq, N, Tp, C, Tp, True)           # dQ[i][c] = sum_j dS[i][j] K[j][c]
         dk = torch.empty_like(k)
-        _gemm_tn(ds, q, dk, N, T, C, T, False)             # dK[j][c] = sum_i dS[i][j] Q[i][c]
+        _gemm_tn(ds, q, dk, N, Tp, C, Tp, False)           # dK[j][c] = sum_i dS[i][j] Q[i][c]
+        if Tp != T:
+            dq, dk, dv = (t[:, :T].reshape(shape) for t in (dq, dk, dv))
         return dq, dk, dv
 
 
