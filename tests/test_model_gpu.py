@@ -144,7 +144,8 @@ def test_ragged_image_sizes_match_oracle(vcd, pair, monkeypatch, H, W, B):
     record_parity(f"test_model_gpu ragged H={H} W={W} B={B} params=fp32", measured)
     assert measured["latent mean"] < 2.75e-2 and measured["reconstruction"] < 4.0e-2, measured
     assert measured["rec_loss"] < 1e-2 and measured["kl"] < 1e-2, measured
-    assert measured["grad_median"] < 3.4e-2 and measured["grad_max"] < 0.2, measured
+    # measured on B200 (profiles/r02_parity.json): grad median 0.9-1.9e-2, max 4.5-5.1e-2 over the 245 tensors with a gradient
+    assert measured["grad_median"] < 3.4e-2 and measured["grad_max"] < 8e-2, measured
 
 
 def test_eval_mode_path_and_wrapper(vcd, pair):
