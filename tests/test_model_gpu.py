@@ -493,3 +493,61 @@ def test_graphed_step_survives_zero_grad_set_to_none(vcd, pair):
     assert not torch.equal(before, w.vae.decoder.conv_out.weight.detach())
     assert float(slot.scal[2]) == 2.0
     mon.remove_hooks()
+
+
+def _grad_errs(model, oracle, scale=1.0):
+    og = dict(oracle.named_parameters())
+    big = max(float(p.grad.norm()) for p in og.values())
+    keep = [n for n, p in og.items() if float(p.grad.norm()) > 1e-4 * big]
+    named = dict(model.named_parameters())
+    return torch.tensor([rel_err(named[n].grad.float() / scale, og[n].grad) for n in keep])
+
+
+def test_usage_patterns_keep_the_producer_consumer_handoffs_consistent(vcd, pair, monkeypatch):
+    """Call orders the reference's callers do not use but torch allows: (a) two forwards, then ONE backward of the summed
+    losses (the second encode() clears the first graph's fused hand-offs: its backward must fall back to the unfused kernels
+    and stay correct); (b) backward twice through one graph (retain_graph) accumulates exactly twice the gradient; (c) a
+    second model instance stepping between forward and backward of the first (the hand-off tables are keyed by live tensors,
+    not by model).  Gradients against the fp32 oracle at the network gates."""
+    from oracle.torch_vae import oracle_forward, oracle_losses
+    oracle, model = pair
+    torch.manual_seed(13)
+    xs = [torch.rand(2, 3, 64, 64, device="cuda") * 2 - 1 for _ in range(2)]
+
+    def our_loss(m, x):
+        d = m.encode(x).latent_dist
+        rec = m.decode(d.mode()).sample
+        return vcd.vae_loss({"reconstruction": rec, "latent_dist": d}, x, 1e-6)[0]
+
+    def oracle_loss(x):
+        return oracle_losses(oracle_forward(oracle, x, False), x, 1e-6)[0]
+
+    # (a) two forwards, one backward
+    oracle.zero_grad(set_to_none=True)
+    model.zero_grad(set_to_none=True)
+    (oracle_loss(xs[0]) + oracle_loss(xs[1])).backward()
+    (our_loss(model, xs[0]) + our_loss(model, xs[1])).backward()
+    e = _grad_errs(model, oracle)
+    assert float(e.median()) < 3.4e-2 and float(e.max()) < 0.1, ("two forwards, one backward", float(e.median()), float(e.max()))
+    # (b) backward twice through one graph
+    oracle.zero_grad(set_to_none=True)
+    model.zero_grad(set_to_none=True)
+    oracle_loss(xs[0]).backward()
+    l = our_loss(model, xs[0])
+    l.backward(retain_graph=True)
+    l.backward()
+    e = _grad_errs(model, oracle, scale=2.0)
+    assert float(e.median()) < 3.4e-2 and float(e.max()) < 0.1, ("backward twice", float(e.median()), float(e.max()))
+    # (c) another instance runs a whole step between this model's forward and backward
+    other = vcd.B200AutoencoderKL().cuda()
+    other.load_state_dict(oracle.state_dict())
+    model.zero_grad(set_to_none=True)
+    l = our_loss(model, xs[0])
+    our_loss(other, xs[1]).backward()
+    l.backward()
+    e = _grad_errs(model, oracle)
+    assert float(e.median()) < 3.4e-2 and float(e.max()) < 0.1, ("interleaved instances", float(e.median()), float(e.max()))
+    oracle.zero_grad(set_to_none=True)
+    oracle_loss(xs[1]).backward()
+    e = _grad_errs(other, oracle)
+    assert float(e.median()) < 3.4e-2 and float(e.max()) < 0.1, ("second instance", float(e.median()), float(e.max()))
