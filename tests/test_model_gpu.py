@@ -106,11 +106,11 @@ def test_forward_backward_matches_oracle(vcd, pair, monkeypatch, impl, R, B):
         vcd.ops.set_conv_impl(vcd._lib.IMPL_AUTO)
 
 
-@pytest.mark.parametrize("H,W,B", [(88, 72, 3), (136, 200, 1), (264, 312, 1)])
+@pytest.mark.parametrize("H,W,B", [(88, 72, 3), (136, 200, 1), (264, 312, 1), (32, 32, 5), (24, 8, 3)])
 def test_ragged_image_sizes_match_oracle(vcd, pair, monkeypatch, H, W, B):
     """Sizes that are multiples of 8 only (the three downsamplers) but of none of the kernel tiles: partial 8x16 halo tiles
     (TMA zero fill, masked stores), an odd number of tiles per image (the second CTA of the last pair idles), levels below the
-    halo kernel's minimum (11 x 9 at 88 x 72), 33 x 39 tokens in the attention block, odd batch.  Forward, losses and all 248
+    halo kernel's minimum (11 x 9 at 88 x 72), 33 x 39 / 3 x 1 tokens in the attention block, odd batch.  Forward, losses and all 248
     gradients against the fp32 oracle at the network-level gates of test_forward_backward_matches_oracle."""
     from oracle.torch_vae import oracle_forward, oracle_losses
     oracle, model = pair
