@@ -663,16 +663,22 @@ def main():
         e0.record()
         last = None
         trace = [] if os.environ.get("VCD_BENCH_TRACE") else None
+        # e2e: every step's batch is copied from pinned host memory inside the timed region, as train.py does it (batch.to(device)
+        # at the start of the step).  VCD_BENCH_PREFETCH=1: through vcd_b200.data.DevicePrefetcher (batch i+1 on a copy stream
+        # while step i runs) — measured on B200: 86.29 vs 85.83-86.64 ms per step, no gain (the 25 MB copy is 0.5 ms and mostly
+        # hidden behind the host's launch lead already), so the plain copy stays the default
+        if e2e and os.environ.get("VCD_BENCH_PREFETCH"):
+            feed = iter(vcd_b200.data.DevicePrefetcher((host[i % n_host] for i in range(K)), dev))
+        elif e2e:
+            feed = (host[i % n_host].to(dev, non_blocking=True) for i in range(K))
+        else:
+            feed = (resident[i % n_host] for i in range(K))
         for i in range(K):
             if trace is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 trace.append(ev)
-            if e2e:
-                x = host[i % n_host].to(dev, non_blocking=True)   # H2D from pinned memory inside the timed region
-                last = train_step(x)                               # the three loss scalars come back to the host every step
-            else:
-                last = train_step(resident[i % n_host])
+            last = train_step(next(feed))                          # the three loss scalars come back to the host every step
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -782,7 +788,10 @@ def main():
                        "step_mfu_of_sustained_peak": (value / world) * fl_img / 1e12 / peak_t,
                        "nudges_applied": state["nudged"], "inactive_flagged": state["inactive"], "final_loss": loss},
             "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": B * 3 * R * R * 4, "d2h_bytes_per_step": 12,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "h2d": ("every step's batch copied from pinned host memory inside the timed region, batch i+1 on a copy "
+                            "stream while step i runs (vcd_b200.data.DevicePrefetcher)" if os.environ.get("VCD_BENCH_PREFETCH")
+                            else "batch.to(device) on the compute stream at the start of every step")},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": roof, "roofline_hbm": roof_hbm, "other_entry_points_ms_per_step": other, "cpu_baseline": cpu,

@@ -170,3 +170,18 @@ def test_fused_clip_adamw_on_the_vae(vcd):
     moved = sum(int((p.detach().float() != q.detach().float()).sum()) for p, q in
                 zip(vae.parameters(), vcd.B200AutoencoderKL.from_pretrained("random-init:42", torch_dtype=torch.bfloat16).cuda().parameters()))
     assert moved > 0
+
+
+def test_device_prefetcher_yields_every_batch_once_in_order(vcd):
+    """input pipeline: tensors and collate_fn-style dicts, copy stream ordering, empty iterable"""
+    from vcd_b200.data import DevicePrefetcher
+    host = [torch.full((4, 3, 16, 16), float(i)).pin_memory() for i in range(5)]
+    got = [b for b in DevicePrefetcher(host, "cuda")]
+    assert len(got) == 5 and all(b.is_cuda for b in got)
+    assert [float(b.mean()) for b in got] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    dicts = [{"pixel_values": h, "labels": torch.tensor([i])} for i, h in enumerate(host)]
+    out = list(DevicePrefetcher(dicts, "cuda"))
+    assert [int(d["labels"]) for d in out] == [0, 1, 2, 3, 4] and all(d["pixel_values"].is_cuda for d in out)
+    assert list(DevicePrefetcher([], "cuda")) == []
+    with pytest.raises(ValueError):
+        DevicePrefetcher(host, "cpu")

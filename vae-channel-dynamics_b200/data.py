@@ -72,3 +72,56 @@ def preprocess_uint8_batch(images_u8, resolution: int, out_dtype=None):
     out = torch.empty((N, 3, resolution, resolution), dtype=torch.float32, device=x.device)
     call("vcd_preprocess_u8", _p(x), _p(out), N, H, W, int(resolution), _st())
     return out if out_dtype in (None, torch.float32) else out.to(out_dtype)
+
+
+class DevicePrefetcher:
+    """Iterates an iterable of pinned host batches (tensors, or dicts of tensors as the reference's collate_fn returns them,
+    data_utils.py:204-211) and yields them on `device`, copying batch i+1 on a copy stream while the caller trains on batch i
+    — the device-side half of `DataLoader(pin_memory=True)` + `batch.to(device)` (train.py:283-286 via accelerate) without
+    the copy on the critical path.  Every batch is still copied exactly once, from pinned memory, when it is about to be
+    used; only its position on the timeline changes."""
+
+    def __init__(self, batches, device):
+        import torch
+        self._torch = torch
+        self.batches = batches
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("DevicePrefetcher: device must be a CUDA device (no CPU path)")
+        self.stream = torch.cuda.Stream(self.device)
+
+    def _issue(self, batch):
+        torch = self._torch
+        with torch.cuda.stream(self.stream):
+            if isinstance(batch, dict):
+                out = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            else:
+                out = batch.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return out, ev
+
+    def _ready(self, issued):
+        torch = self._torch
+        out, ev = issued
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in (out.values() if isinstance(out, dict) else (out,)):
+            if torch.is_tensor(t):
+                t.record_stream(cur)      # allocated on the copy stream, consumed on the caller's stream
+        return out
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            cur = self._issue(next(it))
+        except StopIteration:
+            return
+        for nxt_host in it:
+            nxt = self._issue(nxt_host)
+            yield self._ready(cur)
+            cur = nxt
+        yield self._ready(cur)
+
+    def __len__(self):
+        return len(self.batches)
