@@ -729,6 +729,19 @@ def main():
             prev = dt
             if steady:
                 break
+    if os.environ.get("VCD_BENCH_AB") and world == 1:
+        # profiling aid: VCD_BENCH_AB="VAR=a,b" times --steps steps under VAR=a and VAR=b alternately (3 rounds) inside this
+        # one process — same box, same thermal state — for knobs the host side reads at run time (e.g. VCD_WGRAD_OVERLAP)
+        var, vals = os.environ["VCD_BENCH_AB"].split("=")
+        res_ab = {v: [] for v in vals.split(",")}
+        for _ in range(3):
+            for v in res_ab:
+                os.environ[var] = v
+                train_step(resident[0])
+                res_ab[v].append(timed(args.steps, e2e=False)[0] / args.steps)
+        print("[ab] " + var + ": " + "; ".join(f"{v}: " + " ".join(f"{t:.2f}" for t in ts) + f" (min {min(ts):.2f}) ms/step"
+                                                 for v, ts in res_ab.items()), file=sys.stderr, flush=True)
+        os.environ.pop(var, None)
     clocks.rows.clear()   # keep only the samples of the timed region
     ms, launches, loss = timed(args.steps, e2e=False)
     ms_e2e, _, loss_e2e = (ms, 0, loss) if args.quick else timed(args.steps, e2e=True)

@@ -37,6 +37,11 @@ typedef void* vcd_stream_t; /* cudaStream_t */
 #define VCD_IMPL_AUTO 0
 #define VCD_IMPL_SIMT 1 /* CUDA-core direct convolution (small-channel layers, cross-check) */
 #define VCD_IMPL_UMMA 2 /* tcgen05/TMEM/TMA implicit GEMM; error if the shape is unsupported */
+/* flag OR-ed into the `impl` argument of vcd_conv2d_wgrad: the caller has already zeroed the workspace with
+ * vcd_conv2d_wgrad_prepare() and enqueued, after it and directly before this call, a kernel that neither writes x / dy
+ * nor reads dw / db / ws (the data-gradient GEMM of the same layer): the weight-gradient GEMM is then launched as a
+ * programmatic dependent launch and its CTAs fill the SMs which that kernel's last wave leaves idle. */
+#define VCD_WGRAD_OVERLAP_PREV 0x100
 
 const char* vcd_last_error(void);
 int vcd_version(void);
@@ -104,12 +109,14 @@ int vcd_conv2d_dgrad_gn(const void* dy, const void* w_dgrad, void* g_out, int N,
                         const void* gn_gamma, const void* gn_beta, int param_dtype, int gn_groups, float gn_eps,
                         int gn_act, float* gn_dsdb, float* gn_ab_ws, vcd_stream_t stream);
 /* dw (OIHW, `dtype`) and db ([Cout], `dtype`, may be NULL).  ws: workspace of vcd_conv2d_wgrad_ws_bytes()
- * bytes (zeroed by the call).  db_colsum (fp32 [Cout], may be NULL): column sums of dy already produced by
+ * bytes (zeroed by the call unless VCD_WGRAD_OVERLAP_PREV is set).  db_colsum (fp32 [Cout], may be NULL): column sums of dy already produced by
  * the kernel that wrote dy (vcd_gn_bwd_apply), which saves the bias-gradient pass over dy. */
 int64_t vcd_conv2d_wgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
 int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, const float* db_colsum, int dtype, void* ws,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_t, int pad_l,
                      int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream);
+/* zeroes the accumulators inside ws ahead of a vcd_conv2d_wgrad(..., impl | VCD_WGRAD_OVERLAP_PREV, ...) call */
+int vcd_conv2d_wgrad_prepare(void* ws, int Cin, int Cout, int KH, int KW, vcd_stream_t stream);
 
 /* ---- Upsample2D fused: nearest x2 + conv3x3(pad 1) as four 2x2 phase convolutions on the low-resolution
  * tensor with pre-summed weights ([upstream] Upsample2D in decoder.up_blocks.{0,1,2}.upsamplers.0).

@@ -252,3 +252,41 @@ def test_groupnorm_backward_fused_into_conv_dgrad(vcd, N, H, W, C, cout, split):
         assert rel_err(a, r) < 2e-2, name
     for a, r, name in ((dx1, dx0, "dx"), (dg1, dg0, "dgamma"), (db1, db0, "dbeta")):
         assert rel_err(a, r) < 1e-2, name + " fused vs unfused"
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,stride", [
+    (8, 64, 64, 512, 512, 3, 1),     # 256 dgrad items on 74 clusters: a ragged last wave for the weight gradient to fill
+    (4, 128, 128, 128, 128, 3, 1),   # tap-pair wgrad on the single-CTA kernel behind a B-resident dgrad
+    (2, 64, 64, 256, 128, 1, 1),     # 1x1 shortcut
+    (2, 64, 64, 256, 256, 3, 2),     # Downsample2D
+    (2, 12, 10, 128, 3, 3, 1),       # conv_out class: the flag only skips the zeroing (no tcgen05 wgrad)
+])
+def test_wgrad_overlap_modes_agree(vcd, monkeypatch, N, H, W, cin, cout, k, stride):
+    """VCD_WGRAD_OVERLAP = off | stream | pdl (programmatic dependent launch behind the dgrad kernel, the default) give
+    the same gradients: dx bit-identical (no atomics on that path), dw / db equal up to the order of the fp32 split-K
+    atomics; repeated so that a race between the overlapped kernels would show."""
+    ops = vcd.ops
+    pad = 1 if (k == 3 and stride == 1) else 0
+    x = nhwc(bf16_round(torch.randn(N, cin, H, W, device="cuda")))
+    w0 = torch.randn(cout, cin, k, k, device="cuda") / math.sqrt(cin * k * k)
+    b0 = torch.randn(cout, device="cuda") * 0.1
+    Ho, Wo = (H // 2, W // 2) if stride == 2 else (H, W)
+    g = nhwc(bf16_round(torch.randn(N, cout, Ho, Wo, device="cuda")))
+
+    def run(mode):
+        monkeypatch.setenv("VCD_WGRAD_OVERLAP", mode)
+        xp = x.clone().requires_grad_()
+        w, b = w0.clone().requires_grad_(), b0.clone().requires_grad_()
+        y = ops.conv2d(xp, w, b, ops.PackedWeights(), stride=stride, pad_t=pad, pad_l=pad, out_hw=(Ho, Wo))
+        y.backward(g)
+        torch.cuda.synchronize()
+        return xp.grad, w.grad, b.grad
+
+    dx0, dw0, db0 = run("off")
+    assert float(dw0.abs().max()) > 0
+    for mode in ("pdl", "stream", "pdl", "pdl"):
+        for _ in range(3):
+            dx, dw, db = run(mode)
+            assert torch.equal(dx, dx0), mode
+            assert rel_err(dw, dw0) < 1e-4, (mode, rel_err(dw, dw0))
+            assert rel_err(db, db0) < 1e-4, (mode, rel_err(db, db0))

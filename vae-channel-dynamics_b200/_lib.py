@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("VCD_LIB_PATH") or os.path.join(_HERE, "libvcd_b200.so
 
 F32, BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
+WGRAD_OVERLAP_PREV = 0x100   # flag OR-ed into `impl` of vcd_conv2d_wgrad (include/vcd.h)
 
 _p, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
@@ -31,6 +32,7 @@ SIGNATURES = {
     "vcd_conv2d_dgrad_gn": (_i, [_p] * 3 + [_i] * 9 + [_p] * 4 + [_i, _i, _f, _i, _p, _p, _p]),
     "vcd_conv2d_wgrad_ws_bytes": (_i64, [_i] * 8),
     "vcd_conv2d_wgrad": (_i, [_p] * 5 + [_i] + [_p] + [_i] * 14 + [_p]),
+    "vcd_conv2d_wgrad_prepare": (_i, [_p, _i, _i, _i, _i, _p]),
     "vcd_pack_upconv_weight": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "vcd_upconv2d_fprop": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "vcd_upconv2d_dgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),

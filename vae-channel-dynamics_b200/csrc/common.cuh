@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/vcd.h"
 
 typedef __nv_bfloat16 bf16;
@@ -42,6 +44,32 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 int vcd_num_sms();
 // per-DEVICE one-time flags (cudaFuncSetAttribute applies to the current device's context only): slot in [0, 16)
 bool* vcd_device_once(int slot);
+
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// vcd_launch(..., overlap_prev = true) launches with cudaLaunchAttributeProgrammaticStreamSerialization: the grid may start
+// while the kernel enqueued before it in the same stream is still running — as soon as every CTA of that kernel has executed
+// vcd_pdl_trigger() (griddepcontrol.launch_dependents) or exited — and its CTAs then take the SMs the earlier kernel's tail
+// leaves idle.  The launched kernel never executes griddepcontrol.wait, so it must not read anything the earlier kernel
+// writes nor write anything it reads; everything enqueued before THAT kernel is complete, and any later plain launch waits
+// for both.  Used for weight-gradient GEMMs behind the data-gradient GEMM of the same layer (VCD_WGRAD_OVERLAP_PREV).
+template <typename... P, typename... A>
+static inline cudaError_t vcd_launch(void (*kernel)(P...), int grid, int block, size_t smem, cudaStream_t st,
+                                     bool overlap_prev, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = overlap_prev ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void vcd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---- device helpers ---------------------------------------------------------------
 // eight bf16 values moved as ONE 128-bit access (LDG.E.128 / STG.E.128; a struct of bfloat162 is split

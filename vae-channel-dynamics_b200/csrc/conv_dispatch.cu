@@ -340,7 +340,7 @@ int umma_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, in
 
 // ws: zeroed fp32 [tap][Cout][Cin]
 int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, int Cin, int Cout, int KH, int KW,
-               int stride, int pad_t, int pad_l, int Ho, int Wo, int x_planes, cudaStream_t st) {
+               int stride, int pad_t, int pad_l, int Ho, int Wo, int x_planes, cudaStream_t st, bool overlap_prev = false) {
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.form = 1;
@@ -375,7 +375,7 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
     if (stride == 1 || es == 2) rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n, es);
     else rc = make_act_map(&mB, x, Cin, W / 2, H / 2, 4, N, 64, p.tile_w, p.tile_h, p.tile_n);
     if (rc) return rc;
-    return pair_wgrad_launch(mA, mB, q, bn, st);
+    return pair_wgrad_launch(mA, mB, q, bn, st, overlap_prev);
   }
   // Cin = 128: one 256-column tile = two taps (umma_gemm.cuh tap_pairs)
   const bool pairs = Cin == 128 && p.ntaps > 1;
@@ -401,7 +401,7 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
   if (stride == 1 || es == 2) rc = make_act_map(&mB, x, Cin, W, H, 1, N, 64, p.tile_w, p.tile_h, p.tile_n, es);
   else rc = make_act_map(&mB, x, Cin, W / 2, H / 2, 4, N, 64, p.tile_w, p.tile_h, p.tile_n);
   if (rc) return rc;
-  return umma_launch(mA, mB, p, bn_eff, st);
+  return umma_launch(mA, mB, p, bn_eff, st, overlap_prev);
 }
 
 
@@ -986,15 +986,17 @@ extern "C" int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* d
                                 int pad_l, int Ho, int Wo, int x_planes, int impl, vcd_stream_t stream) {
   VCD_CHECK_ARG(x && dy && dw && ws, "conv wgrad: null pointer");
   cudaStream_t st = as_stream(stream);
+  const bool overlap_prev = (impl & VCD_WGRAD_OVERLAP_PREV) != 0;   // ws zeroed by vcd_conv2d_wgrad_prepare
+  impl &= ~VCD_WGRAD_OVERLAP_PREV;
   const int taps = KH * KW;
   const int64_t main_elems = (int64_t)taps * Cout * Cin;
-  VCD_CUDA(cudaMemsetAsync(ws, 0, (size_t)(main_elems + Cout) * sizeof(float), st));
+  if (!overlap_prev) VCD_CUDA(cudaMemsetAsync(ws, 0, (size_t)(main_elems + Cout) * sizeof(float), st));
   float* wsf = (float*)ws;
   const int path = impl == VCD_IMPL_SIMT ? 1 : wgrad_path(Cin, Cout, KH, KW, stride);
   if (impl == VCD_IMPL_UMMA) VCD_CHECK_ARG(path != 1, "conv wgrad: shape has no tcgen05 path");
   int rc;
   if (path == 2) {
-    rc = umma_wgrad(x, dy, wsf, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, x_planes, st);
+    rc = umma_wgrad(x, dy, wsf, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, x_planes, st, overlap_prev);
   } else if (path == 4) {
     VCD_CHECK_ARG(!x_planes, "conv wgrad: parity-plane input only on the tcgen05 stride-2 path");
     const bool small_in = Cin <= 8 && patch_ok(Cin, Cout, stride, taps);
@@ -1021,6 +1023,12 @@ extern "C" int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* d
   if (rc) return rc;
   if (db && !db_colsum && (rc = conv_bias_grad(dy, wsf + main_elems, (int64_t)N * Ho * Wo, Cout, st))) return rc;
   return conv_wgrad_finalize(wsf, db ? db_colsum : nullptr, dw, db, dtype, Cout, Cin, taps, st);
+}
+
+extern "C" int vcd_conv2d_wgrad_prepare(void* ws, int Cin, int Cout, int KH, int KW, vcd_stream_t stream) {
+  VCD_CHECK_ARG(ws != nullptr, "conv wgrad prepare: null workspace");
+  VCD_CUDA(cudaMemsetAsync(ws, 0, (size_t)((int64_t)KH * KW * Cout * Cin + Cout) * sizeof(float), as_stream(stream)));
+  return 0;
 }
 
 // D[b][m][n] = alpha * sum_k A[b][m][k] B[(b)][n][k] (+bias[n]) (+residual[b][m][n])

@@ -82,6 +82,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  vcd_pdl_trigger();   // see umma_pair_kernel: lets a VCD_WGRAD_OVERLAP_PREV launch behind this kernel start early
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -351,7 +352,8 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int P, i
   return 0;
 }
 
-int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p_in, int block_n, cudaStream_t st) {
+int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p_in, int block_n, cudaStream_t st,
+                bool overlap_prev) {
   UmmaParams p = p_in;
   static int rel = -1;
   if (rel < 0) { const char* e = getenv("VCD_GEMM_RELEASE"); rel = (e && e[0] == '1') ? 1 : 0; }
@@ -365,7 +367,7 @@ int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaPara
                                     Cfg<256>::kSmemBytes));
       attr = true;
     }
-    umma_gemm_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(mapA, mapB, p);
+    VCD_CUDA(vcd_launch(umma_gemm_kernel<256>, grid, kThreads, Cfg<256>::kSmemBytes, st, overlap_prev, mapA, mapB, p));
   } else if (block_n == 128) {
     bool& attr = *vcd_device_once(1);
     if (!attr) {
@@ -373,7 +375,7 @@ int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaPara
                                     Cfg<128>::kSmemBytes));
       attr = true;
     }
-    umma_gemm_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(mapA, mapB, p);
+    VCD_CUDA(vcd_launch(umma_gemm_kernel<128>, grid, kThreads, Cfg<128>::kSmemBytes, st, overlap_prev, mapA, mapB, p));
   } else {
     vcd_set_error("umma_launch: BLOCK_N %d unsupported", block_n);
     return -1;

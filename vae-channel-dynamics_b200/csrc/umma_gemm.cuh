@@ -59,7 +59,8 @@ struct UmmaParams {
   int release_arrive;  // A/B knob (VCD_GEMM_RELEASE=1): hand accumulator stages back with a releasing arrive
 };
 
-int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p, int block_n, cudaStream_t st);
+int umma_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const UmmaParams& p, int block_n, cudaStream_t st,
+                bool overlap_prev = false);
 
 // activation map: dims (C, W, H, P, N); strides derive from a dense [N][P][H][W][C] bf16 tensor.
 // es = 2: the box samples every second pixel along W and H (TMA element strides), so a coordinate (2*w + pw, 2*h + ph)

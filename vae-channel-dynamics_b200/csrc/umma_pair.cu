@@ -160,6 +160,9 @@ umma_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int rank = (int)cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
+  // a weight-gradient GEMM enqueued behind this kernel with VCD_WGRAD_OVERLAP_PREV may start filling SMs as soon as this
+  // grid's clusters retire (no effect on plain launches)
+  vcd_pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kAStages; ++s) {
@@ -870,7 +873,8 @@ int pair_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairParams& p,
   return 0;
 }
 
-int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgradParams& p, int block_n, cudaStream_t st) {
+int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgradParams& p, int block_n, cudaStream_t st,
+                      bool overlap_prev) {
   p.total_items = p.ntaps * p.n_tiles * p.m_pairs * p.splits;
   if (p.total_items <= 0) return 0;
   if (p.a_es != 2) p.a_es = 1;
@@ -888,14 +892,14 @@ int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgra
                                     WCfg<256>::kSmemBytes));
       *attr_set[0] = true;
     }
-    umma_pair_wgrad_kernel<256><<<grid, kThreads, WCfg<256>::kSmemBytes, st>>>(mapA, mapB, p);
+    VCD_CUDA(vcd_launch(umma_pair_wgrad_kernel<256>, grid, kThreads, WCfg<256>::kSmemBytes, st, overlap_prev, mapA, mapB, p));
   } else if (block_n == 128) {
     if (!*attr_set[1]) {
       VCD_CUDA(cudaFuncSetAttribute(umma_pair_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     WCfg<128>::kSmemBytes));
       *attr_set[1] = true;
     }
-    umma_pair_wgrad_kernel<128><<<grid, kThreads, WCfg<128>::kSmemBytes, st>>>(mapA, mapB, p);
+    VCD_CUDA(vcd_launch(umma_pair_wgrad_kernel<128>, grid, kThreads, WCfg<128>::kSmemBytes, st, overlap_prev, mapA, mapB, p));
   } else {
     vcd_set_error("pair_wgrad_launch: BLOCK_N %d unsupported", block_n);
     return -1;

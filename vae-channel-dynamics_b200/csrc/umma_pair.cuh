@@ -106,7 +106,9 @@ struct PairWgradParams {
   uint32_t idesc;
   int total_items;
 };
-int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgradParams& p, int block_n, cudaStream_t st);
+// overlap_prev: programmatic dependent launch behind the preceding kernel of the stream (common.cuh vcd_launch)
+int pair_wgrad_launch(const CUtensorMap& mapA, const CUtensorMap& mapB, PairWgradParams& p, int block_n, cudaStream_t st,
+                      bool overlap_prev = false);
 
 // fills mode / tiling / groups / taps / descriptors of a HALO launch; returns false when the shape is not eligible
 bool pair_setup_halo(PairParams& p, int W, int H, int N, const PairTap* taps, int ntaps, int block_n, int* box_h_out);

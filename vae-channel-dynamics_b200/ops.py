@@ -298,9 +298,28 @@ _WGRAD_STREAMS = {}
 wgrad_side_stream_enabled = True      # bench.py switches it off while it times every call with CUDA events
 
 
+def _wgrad_overlap_mode() -> str:
+    """How the weight-gradient GEMM of a conv overlaps the data-gradient GEMM of the same layer (VCD_WGRAD_OVERLAP):
+    "stream" (default) the fork / join onto a side stream described above;
+    "pdl"    one stream: workspace zeroed first, then dgrad, then wgrad as a programmatic dependent launch
+             (VCD_WGRAD_OVERLAP_PREV, include/vcd.h) whose clusters fill the SMs dgrad's last wave leaves idle — no
+             event record / wait per layer;
+    "off"    strictly one after the other.
+    Same-process A/B on B200 (bench.py VCD_BENCH_AB, 512^2 B=8, 3 x 15 steps each): stream 86.98-87.79 ms per step, pdl
+    87.90-88.61, off 88.31-88.71 — the side stream also hides the HBM-bound bias-gradient column sums and the finalize
+    kernels behind the tensor-bound dgrad, which a dependent launch on one stream cannot, so it stays the default.
+    bench.py switches any overlap off (wgrad_side_stream_enabled) while it times every call with CUDA events."""
+    import os
+    if not wgrad_side_stream_enabled or os.environ.get("VCD_WGRAD_STREAM", "1") != "1":
+        return "off"
+    return os.environ.get("VCD_WGRAD_OVERLAP", "stream")
+
+
 def _wgrad_side_stream(device):
     import os
     if not wgrad_side_stream_enabled or os.environ.get("VCD_WGRAD_STREAM", "1") != "1":
+        return None
+    if _wgrad_overlap_mode() != "stream":
         return None
     st = _WGRAD_STREAMS.get(device)
     if st is None:
@@ -361,6 +380,9 @@ class _ConvFn(torch.autograd.Function):
                 # sums).  They must stay referenced until the join below is enqueued — freed earlier, the caching allocator
                 # would hand their memory to the main-stream allocations of this very backward (dx, dsdb), racing the read.
                 dw, db, keep = _ConvFn._wgrad(ctx, xs, dy, weight, bias)
+        pdl = None
+        if side is None and need_w and ctx.needs_input_grad[0] and _wgrad_overlap_mode() == "pdl":
+            pdl = _ConvFn._wgrad_alloc(ctx, dy, weight, bias)     # zeroes the workspace BEFORE the dgrad kernel
         if ctx.needs_input_grad[0]:
             if ctx.gn_info is not None:
                 gx, gsums, ggamma, gbeta, geps, gact, ggroups = ctx.gn_info
@@ -379,21 +401,32 @@ class _ConvFn(torch.autograd.Function):
         if side is not None:      # join: everything after this backward node is ordered after the weight gradient
             torch.cuda.current_stream(dy.device).wait_stream(side)
         elif need_w:
-            dw, db, _ = _ConvFn._wgrad(ctx, xs, dy, weight, bias)
+            dw, db, _ = _ConvFn._wgrad(ctx, xs, dy, weight, bias, pdl)
         del keep
         dres = dy if ctx.has_res and ctx.needs_input_grad[3] else None
         return dx, dw, db, dres, None, None, None, None, None, None, None
 
     @staticmethod
-    def _wgrad(ctx, xs, dy, weight, bias):
+    def _wgrad_alloc(ctx, dy, weight, bias, prepare=True):
         N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl = ctx.cfg
         dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
         db = None if bias is None else torch.empty_like(bias)
         nbytes = _lib.lib().vcd_conv2d_wgrad_ws_bytes(N, H, W, Cin, Cout, KH, KW, stride)
         ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
+        if prepare:
+            call("vcd_conv2d_wgrad_prepare", _p(ws), Cin, Cout, KH, KW, _st())
+        return dw, db, ws
+
+    @staticmethod
+    def _wgrad(ctx, xs, dy, weight, bias, prepared=None):
+        """prepared = (dw, db, ws) of _wgrad_alloc issued BEFORE the dgrad kernel that directly precedes this call in the
+        stream: the GEMM is launched with VCD_WGRAD_OVERLAP_PREV and starts while that kernel's last wave drains."""
+        N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl = ctx.cfg
+        dw, db, ws = prepared if prepared is not None else _ConvFn._wgrad_alloc(ctx, dy, weight, bias, prepare=False)
         colsum = pop_colsum(dy) if db is not None else None
         call("vcd_conv2d_wgrad", _p(xs), _p(dy), _p(dw), _p(db), _p(colsum), dtype_code(weight), _p(ws), N, H, W, Cin, Cout,
-             KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl, _st())
+             KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl | (_lib.WGRAD_OVERLAP_PREV if prepared is not None else 0),
+             _st())
         return dw, db, colsum
 
 
