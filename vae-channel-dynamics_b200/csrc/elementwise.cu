@@ -327,67 +327,115 @@ extern "C" int vcd_pack_conv_weight(const void* w, const void* bias, int dtype, 
 }
 
 // ---------------------------------------------------------------- all weight packs of the model in ONE launch
-// One block = a 16 (Cout) x 64 (Cin) tile of one layer, all taps: coalesced reads of the OIHW rows into shared memory
-// (fp32), then the fprop pack [tap][Cout][Cin] (128-byte row segments), the dgrad pack [tap][Cin][Cout] (32-byte
-// segments) and, for mode 1, the 16 pre-summed phase taps of the Upsample2D form (conv_dispatch.cu).  Replaces ~140
-// per-layer launches of pack_weight_kernel / bias_to_f32_kernel per forward.
+// One block = a 32 (Cout) x 64 (Cin) tile of one layer, all taps: the OIHW rows of the tile (64 x taps contiguous elements
+// per output channel) are read with 16-byte loads into shared memory (fp32), then written as the fprop pack
+// [tap][Cout][Cin] and the dgrad pack [tap][Cin][Cout] with ONE 16-byte store per thread and tap (eight consecutive input /
+// output channels gathered from the tile; 128-byte / 64-byte contiguous segments per row) and, for mode 1, as the 16
+// pre-summed phase taps of the Upsample2D form (conv_dispatch.cu).  HBM-bound: 2 (bf16) or 4 (fp32) bytes read + 4 bytes
+// written per weight = 0.5 GB for the 83.6 M parameters of the VAE.  Partial tiles (the small-channel layers) and
+// misaligned tensors take the element-wise path below.  Replaces ~140 per-layer launches of pack_weight_kernel /
+// bias_to_f32_kernel per forward.
 namespace {
-constexpr int kPackCo = 16, kPackCi = 64;
+constexpr int kPackCo = 32, kPackCi = 64;
+constexpr int kPackRow = kPackCi * 9 + 1;   // floats per tile row (odd: conflict-free column walks)
+constexpr int kPackSmem = kPackCo * kPackRow * (int)sizeof(float);
 __device__ __forceinline__ int up_group_pack(int a, int k) { return a == 0 ? (k == 0 ? 0 : 1) : (k <= 1 ? 0 : 1); }
+// value of output tap q at (co, ci) of the tile: the source tap itself, or the pre-summed phase tap of an Upsample2D conv
+template <int MODE>
+__device__ __forceinline__ float pack_value(const float* __restrict__ trow, int ci, int taps, int q) {
+  if (MODE == 0) return trow[ci * taps + q];
+  const int dw = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
+  float v = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+      if (up_group_pack(a, kh) == dh && up_group_pack(b, kw) == dw) v += trow[ci * 9 + kh * 3 + kw];
+  return v;
+}
+template <int MODE>
+__device__ __forceinline__ void pack_full_tile(const float* __restrict__ tile, const vcd_pack_desc& d, int co0, int ci0) {
+  bf16* wf = reinterpret_cast<bf16*>(d.wf);
+  bf16* wd = reinterpret_cast<bf16*>(d.wd);
+  const int taps = d.taps, otaps = MODE == 1 ? 16 : taps;
+  {   // fprop pack: thread = (output channel, group of 8 input channels)
+    const int ci8 = threadIdx.x & 7, co = threadIdx.x >> 3;
+    const float* trow = tile + co * kPackRow;
+    for (int q = 0; q < otaps; ++q) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = pack_value<MODE>(trow, ci8 * 8 + k, taps, q);
+      st8(wf + ((int64_t)q * d.cout + co0 + co) * d.cin + ci0 + ci8 * 8, pack8(v));
+    }
+  }
+  if (wd == nullptr) return;
+  {   // dgrad pack: thread = (input channel, group of 8 output channels)
+    const int co8 = threadIdx.x & 3, ci = threadIdx.x >> 2;
+    for (int q = 0; q < otaps; ++q) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = pack_value<MODE>(tile + (co8 * 8 + k) * kPackRow, ci, taps, q);
+      st8(wd + ((int64_t)q * d.cin + ci0 + ci) * d.cout + co0 + co8 * 8, pack8(v));
+    }
+  }
+}
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 __global__ void __launch_bounds__(256) multi_pack_kernel(const vcd_pack_desc* __restrict__ descs,
                                                         const int32_t* __restrict__ tile_layer,
                                                         const int32_t* __restrict__ tile_co,
                                                         const int32_t* __restrict__ tile_ci) {
-  __shared__ float tile[kPackCo][kPackCi * 9 + 1];
+  extern __shared__ float tile[];   // [kPackCo][kPackRow]
   const vcd_pack_desc d = descs[tile_layer[blockIdx.x]];
   const int co0 = tile_co[blockIdx.x], ci0 = tile_ci[blockIdx.x];
   const int nco = min(kPackCo, d.cout - co0), nci = min(kPackCi, d.cin - ci0);
   const int taps = d.taps;             // taps of the SOURCE tensor (9 for mode 1)
   const int row = nci * taps;          // contiguous source elements per output channel of this tile
-  for (int i = threadIdx.x; i < nco * row; i += blockDim.x) {
-    const int co = i / row, e = i - co * row;
-    tile[co][e] = load_param(d.w, d.dtype, ((int64_t)(co0 + co) * d.cin + ci0) * taps + e);
+  const bool full = nco == kPackCo && nci == kPackCi && (taps == 9 || taps == 1) && (d.cin & 7) == 0 && (d.cout & 7) == 0 &&
+                    aligned16(d.w) && aligned16(d.wf) && aligned16(d.wd) && (d.mode == 0 || taps == 9);
+  if (full && d.dtype == VCD_F32) {
+    const int nv = row >> 2;
+    for (int i = threadIdx.x; i < kPackCo * nv; i += blockDim.x) {
+      const int co = i / nv, e = (i - co * nv) << 2;
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d.w) +
+                                                        ((int64_t)(co0 + co) * d.cin + ci0) * taps + e);
+      float* t = tile + co * kPackRow + e;
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+  } else if (full) {
+    const int nv = row >> 3;
+    for (int i = threadIdx.x; i < kPackCo * nv; i += blockDim.x) {
+      const int co = i / nv, e = (i - co * nv) << 3;
+      unpack8(ld8(reinterpret_cast<const bf16*>(d.w) + ((int64_t)(co0 + co) * d.cin + ci0) * taps + e),
+              tile + co * kPackRow + e);
+    }
+  } else {
+    for (int i = threadIdx.x; i < nco * row; i += blockDim.x) {
+      const int co = i / row, e = i - co * row;
+      tile[co * kPackRow + e] = load_param(d.w, d.dtype, ((int64_t)(co0 + co) * d.cin + ci0) * taps + e);
+    }
   }
   if (ci0 == 0 && d.bias != nullptr && d.bias_f32 != nullptr)
     for (int i = threadIdx.x; i < nco; i += blockDim.x) d.bias_f32[co0 + i] = load_param(d.bias, d.dtype, co0 + i);
   __syncthreads();
+  if (full) {
+    if (d.mode == 1) pack_full_tile<1>(tile, d, co0, ci0);
+    else pack_full_tile<0>(tile, d, co0, ci0);
+    return;
+  }
+  // element-wise path: partial tiles (small-channel layers), unusual tap counts, misaligned tensors
   bf16* wf = reinterpret_cast<bf16*>(d.wf);
   bf16* wd = reinterpret_cast<bf16*>(d.wd);
   const int otaps = d.mode == 1 ? 16 : taps;
-  // fprop pack: consecutive threads along ci
-  for (int i = threadIdx.x; i < otaps * nco * nci; i += blockDim.x) {
+  for (int i = threadIdx.x; i < otaps * nco * nci; i += blockDim.x) {   // fprop pack: consecutive threads along ci
     const int ci = i % nci, r = i / nci, co = r % nco, q = r / nco;
-    float v;
-    if (d.mode == 1) {
-      const int dw = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
-      v = 0.f;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          if (up_group_pack(a, kh) == dh && up_group_pack(b, kw) == dw) v += tile[co][ci * 9 + kh * 3 + kw];
-    } else {
-      v = tile[co][ci * taps + q];
-    }
+    const float v = d.mode == 1 ? pack_value<1>(tile + co * kPackRow, ci, 9, q) : pack_value<0>(tile + co * kPackRow, ci, taps, q);
     wf[((int64_t)q * d.cout + co0 + co) * d.cin + ci0 + ci] = __float2bfloat16_rn(v);
   }
   if (wd == nullptr) return;
-  // dgrad pack: consecutive threads along co
-  for (int i = threadIdx.x; i < otaps * nco * nci; i += blockDim.x) {
+  for (int i = threadIdx.x; i < otaps * nco * nci; i += blockDim.x) {   // dgrad pack: consecutive threads along co
     const int co = i % nco, r = i / nco, ci = r % nci, q = r / nci;
-    float v;
-    if (d.mode == 1) {
-      const int dw = q & 1, dh = (q >> 1) & 1, b = (q >> 2) & 1, a = (q >> 3) & 1;
-      v = 0.f;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          if (up_group_pack(a, kh) == dh && up_group_pack(b, kw) == dw) v += tile[co][ci * 9 + kh * 3 + kw];
-    } else {
-      v = tile[co][ci * taps + q];
-    }
+    const float v = d.mode == 1 ? pack_value<1>(tile + co * kPackRow, ci, 9, q) : pack_value<0>(tile + co * kPackRow, ci, taps, q);
     wd[((int64_t)q * d.cin + ci0 + ci) * d.cout + co0 + co] = __float2bfloat16_rn(v);
   }
 }
@@ -398,7 +446,12 @@ extern "C" int vcd_pack_tile_ci(void) { return kPackCi; }
 extern "C" int vcd_multi_pack_weights(const vcd_pack_desc* descs, const int32_t* tile_layer, const int32_t* tile_co,
                                       const int32_t* tile_ci, int n_tiles, vcd_stream_t stream) {
   VCD_CHECK_ARG(descs && tile_layer && tile_co && tile_ci && n_tiles > 0, "vcd_multi_pack_weights: bad arguments");
-  multi_pack_kernel<<<n_tiles, 256, 0, as_stream(stream)>>>(descs, tile_layer, tile_co, tile_ci);
+  bool& attr = *vcd_device_once(8);
+  if (!attr) {
+    VCD_CUDA(cudaFuncSetAttribute(multi_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPackSmem));
+    attr = true;
+  }
+  multi_pack_kernel<<<n_tiles, 256, kPackSmem, as_stream(stream)>>>(descs, tile_layer, tile_co, tile_ci);
   VCD_LAUNCH_CHECK();
   return 0;
 }
