@@ -737,11 +737,14 @@ def main():
         for _ in range(3):
             for v in res_ab:
                 os.environ[var] = v
+                if var == "VCD_ZERO_POOL":      # read once at import by ops.py
+                    vcd_b200.ops.zero_pool_enabled = v == "1"
                 train_step(resident[0])
                 res_ab[v].append(timed(args.steps, e2e=False)[0] / args.steps)
         print("[ab] " + var + ": " + "; ".join(f"{v}: " + " ".join(f"{t:.2f}" for t in ts) + f" (min {min(ts):.2f}) ms/step"
                                                  for v, ts in res_ab.items()), file=sys.stderr, flush=True)
         os.environ.pop(var, None)
+        vcd_b200.ops.zero_pool_enabled = os.environ.get("VCD_ZERO_POOL", "1") == "1"
     clocks.rows.clear()   # keep only the samples of the timed region
     ms, launches, loss = timed(args.steps, e2e=False)
     ms_e2e, _, loss_e2e = (ms, 0, loss) if args.quick else timed(args.steps, e2e=True)

@@ -42,6 +42,11 @@ typedef void* vcd_stream_t; /* cudaStream_t */
  * nor reads dw / db / ws (the data-gradient GEMM of the same layer): the weight-gradient GEMM is then launched as a
  * programmatic dependent launch and its CTAs fill the SMs which that kernel's last wave leaves idle. */
 #define VCD_WGRAD_OVERLAP_PREV 0x100
+/* flag: the accumulator buffers this call would zero before its kernels add into them are ALREADY zero (the caller carved
+ * them out of a zero-filled arena), so the call enqueues no memset — a training step otherwise issues ~245 of them, each a
+ * 2 us device activity plus one more launch boundary.  OR-ed into `impl` of vcd_conv2d_fprop (gn_sums) and vcd_conv2d_wgrad
+ * (ws), and into `act_silu` of vcd_gn_bwd_reduce (dsdb) and vcd_gn_bwd_apply (dx_colsum). */
+#define VCD_ACC_PREZEROED 0x200
 
 const char* vcd_last_error(void);
 int vcd_version(void);
@@ -109,7 +114,7 @@ int vcd_conv2d_dgrad_gn(const void* dy, const void* w_dgrad, void* g_out, int N,
                         const void* gn_gamma, const void* gn_beta, int param_dtype, int gn_groups, float gn_eps,
                         int gn_act, float* gn_dsdb, float* gn_ab_ws, vcd_stream_t stream);
 /* dw (OIHW, `dtype`) and db ([Cout], `dtype`, may be NULL).  ws: workspace of vcd_conv2d_wgrad_ws_bytes()
- * bytes (zeroed by the call unless VCD_WGRAD_OVERLAP_PREV is set).  db_colsum (fp32 [Cout], may be NULL): column sums of dy already produced by
+ * bytes (zeroed by the call unless VCD_WGRAD_OVERLAP_PREV or VCD_ACC_PREZEROED is set).  db_colsum (fp32 [Cout], may be NULL): column sums of dy already produced by
  * the kernel that wrote dy (vcd_gn_bwd_apply), which saves the bias-gradient pass over dy. */
 int64_t vcd_conv2d_wgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
 int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* db, const float* db_colsum, int dtype, void* ws,
@@ -171,7 +176,8 @@ int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, float near_z
 int vcd_gn_apply_fwd(const void* x, const double* sums, const void* gamma, const void* beta, int param_dtype,
                      void* out, float* chan_stats_in, float* chan_stats_out, float near_zero, float eps, int act_silu,
                      int N, int HW, int C, int G, vcd_stream_t stream);
-/* backward: dsdb[n][c] = {sum g*x, sum g} with g = dout * silu'(y) ; then dx; then dgamma/dbeta */
+/* backward: dsdb[n][c] = {sum g*x, sum g} with g = dout * silu'(y) ; then dx; then dgamma/dbeta.
+ * act_silu: 1 = SiLU follows the GroupNorm; VCD_ACC_PREZEROED may be OR-ed in (dsdb / dx_colsum already zero). */
 int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* sums, const void* gamma, const void* beta,
                       int param_dtype, float* dsdb, float eps, int act_silu,
                       int N, int HW, int C, int G, vcd_stream_t stream);

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("VCD_LIB_PATH") or os.path.join(_HERE, "libvcd_b200.so
 F32, BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_UMMA = 0, 1, 2
 WGRAD_OVERLAP_PREV = 0x100   # flag OR-ed into `impl` of vcd_conv2d_wgrad (include/vcd.h)
+ACC_PREZEROED = 0x200        # flag: accumulator arguments are already zero, the call enqueues no memset (include/vcd.h)
 
 _p, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 

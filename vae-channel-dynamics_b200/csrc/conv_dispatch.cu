@@ -101,7 +101,8 @@ int attach_gn(PairParams& p, GnEpilogue* gn, int n_images, int Nout, int rows_pe
   if (logD < 0 || Nout % 32 != 0) return 0;
   if (p.mode == 1 && (rows_per_img <= 0 || rows_per_img % 128 != 0)) return 0;
   p.gn_sums = gn->sums; p.gn_G = gn->groups; p.gn_logD = logD; p.gn_rows_per_img = rows_per_img;
-  if (!gn->accumulate) VCD_CUDA(cudaMemsetAsync(gn->sums, 0, sizeof(double) * 2 * n_images * gn->groups, st));
+  if (!gn->accumulate && !gn->prezeroed)
+    VCD_CUDA(cudaMemsetAsync(gn->sums, 0, sizeof(double) * 2 * n_images * gn->groups, st));
   gn->fused = true;
   return 0;
 }
@@ -136,7 +137,6 @@ int try_pair_halo(const void* act, int C, int Wa, int Ha, int P, int N, int Wt, 
   if (gnb) {
     VCD_CHECK_ARG(Nout <= 512 && Nout % 32 == 0, "fused GroupNorm backward: channels must be a multiple of 32, <= 512");
     p.gnb_x = (const bf16*)gnb->x; p.gnb_ab = gnb->ab; p.gnb_dsdb = gnb->dsdb; p.gnb_act = gnb->act;
-    VCD_CUDA(cudaMemsetAsync(gnb->dsdb, 0, sizeof(float) * 2 * N * Nout, st));
   }
   p.a_es = es;
   // 128 -> 128 channel 3x3 layers: the CTA's whole weight operand (ntaps * kc boxes of 8 KB) fits beside two A boxes, so it
@@ -891,12 +891,14 @@ extern "C" int vcd_conv2d_fprop(const void* x, const void* w_fprop, const float*
                                 vcd_stream_t stream) {
   VCD_CHECK_ARG(x && w_fprop && y, "conv fprop: null pointer");
   cudaStream_t st = as_stream(stream);
+  const bool prezeroed = (impl & VCD_ACC_PREZEROED) != 0;
+  impl &= 0xff;
   if (gn_sums) {  // GroupNorm sums of y: fused into the GEMM epilogue when the pair kernel serves the layer
-    GnEpilogue gn{gn_sums, gn_groups, false};
+    GnEpilogue gn{gn_sums, gn_groups, false, false, prezeroed};
     const int rc = conv_fprop_impl(x, w_fprop, bias, residual, y, ws, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho,
                                    Wo, x_planes, impl, &gn, st);
     if (rc || gn.fused) return rc;
-    return vcd_gn_stats(y, gn_sums, nullptr, 0.f, N, Ho * Wo, Cout, gn_groups, stream);
+    return gn_stats_launch(y, gn_sums, nullptr, 0.f, N, Ho * Wo, Cout, gn_groups, st, prezeroed);
   }
   return conv_fprop_impl(x, w_fprop, bias, residual, y, ws, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo,
                          x_planes, impl, nullptr, st);
@@ -925,6 +927,7 @@ extern "C" int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void*
   (void)w_fprop;
   VCD_CHECK_ARG(dy && dx, "conv dgrad: null pointer");
   cudaStream_t st = as_stream(stream);
+  impl &= 0xff;
   const int path = impl == VCD_IMPL_SIMT ? 1 : dgrad_path(Cin, Cout, KH, KW, stride);
   if (impl == VCD_IMPL_UMMA) VCD_CHECK_ARG(path != 1, "conv dgrad: shape has no tcgen05 path");
   if (path == 2)
@@ -958,7 +961,9 @@ extern "C" int vcd_conv2d_dgrad_gn(const void* dy, const void* w_dgrad, void* g_
   VCD_CHECK_ARG(vcd_conv2d_dgrad_gn_supported(N, H, W, Cin, Cout, KH, KW, 1), "conv dgrad+GN: shape not supported");
   cudaStream_t st = as_stream(stream);
   int rc;
-  if ((rc = gn_make_ab(gn_sums, gn_gamma, gn_beta, param_dtype, gn_eps, N, H * W, Cin, gn_groups, gn_ab_ws, st))) return rc;
+  // the kernel that writes (a, b) also zeroes gn_dsdb (same [N][Cin][2] shape): no memset between it and the GEMM
+  if ((rc = gn_make_ab(gn_sums, gn_gamma, gn_beta, param_dtype, gn_eps, N, H * W, Cin, gn_groups, gn_ab_ws, gn_dsdb, st)))
+    return rc;
   GnBwdPrologue gnb{gn_x, gn_ab_ws, gn_dsdb, gn_act};
   PairTap taps[9];
   for (int kh = 0; kh < KH; ++kh)
@@ -987,10 +992,11 @@ extern "C" int vcd_conv2d_wgrad(const void* x, const void* dy, void* dw, void* d
   VCD_CHECK_ARG(x && dy && dw && ws, "conv wgrad: null pointer");
   cudaStream_t st = as_stream(stream);
   const bool overlap_prev = (impl & VCD_WGRAD_OVERLAP_PREV) != 0;   // ws zeroed by vcd_conv2d_wgrad_prepare
-  impl &= ~VCD_WGRAD_OVERLAP_PREV;
+  const bool prezeroed = overlap_prev || (impl & VCD_ACC_PREZEROED) != 0;
+  impl &= 0xff;
   const int taps = KH * KW;
   const int64_t main_elems = (int64_t)taps * Cout * Cin;
-  if (!overlap_prev) VCD_CUDA(cudaMemsetAsync(ws, 0, (size_t)(main_elems + Cout) * sizeof(float), st));
+  if (!prezeroed) VCD_CUDA(cudaMemsetAsync(ws, 0, (size_t)(main_elems + Cout) * sizeof(float), st));
   float* wsf = (float*)ws;
   const int path = impl == VCD_IMPL_SIMT ? 1 : wgrad_path(Cin, Cout, KH, KW, stride);
   if (impl == VCD_IMPL_UMMA) VCD_CHECK_ARG(path != 1, "conv wgrad: shape has no tcgen05 path");

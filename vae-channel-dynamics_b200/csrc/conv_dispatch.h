@@ -12,5 +12,9 @@ int simt_conv_wgrad(const void* x, const void* dy, float* ws, int N, int H, int 
 int conv_bias_grad(const void* dy, float* out, int64_t pixels, int C, cudaStream_t st);
 int conv_wgrad_finalize(const float* ws, const float* bias_src, void* dw, void* db, int dtype, int Cout, int Cin, int taps,
                         cudaStream_t st);
+// ab[n][c] = (a, b) of the affine GroupNorm y = a x + b; zero_dsdb (may be NULL): a [N][C][2] fp32 buffer zeroed in passing
 int gn_make_ab(const double* sums, const void* gamma, const void* beta, int pdt, float eps, int N, int HW, int C, int G,
-               float* ab, cudaStream_t st);
+               float* ab, float* zero_dsdb, cudaStream_t st);
+// vcd_gn_stats with the zeroing of `sums` optional (prezeroed: the caller guarantees it is zero)
+int gn_stats_launch(const void* x, double* sums, float* chan_stats_in, float near_zero, int N, int HW, int C, int G,
+                    cudaStream_t st, bool prezeroed);

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "conv_dispatch.h"
 
 namespace {
 
@@ -534,9 +535,11 @@ __global__ void gn_param_grad_kernel(const double* __restrict__ sums, const floa
 // ab[n][c] = (a, b) with y = a * x + b the affine GroupNorm of image n, channel c (used by the conv dgrad epilogue that
 // applies SiLU' and reduces the GroupNorm backward sums, umma_pair.cu)
 __global__ void gn_ab_kernel(const double* __restrict__ sums, const void* __restrict__ gamma, const void* __restrict__ beta,
-                             int pdt, float eps, int N, int HW, int C, int G, float* __restrict__ ab) {
+                             int pdt, float eps, int N, int HW, int C, int G, float* __restrict__ ab,
+                             float* __restrict__ zero_dsdb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
+  if (zero_dsdb) zero_dsdb[2 * i] = zero_dsdb[2 * i + 1] = 0.f;
   const int n = i / C, c = i - n * C, D = C / G, g = c / D;
   const double cnt = (double)D * (double)HW;
   const double mu = sums[((int64_t)n * G + g) * 2] / cnt;
@@ -587,9 +590,9 @@ GnShape gn_launch_shape(int N, int HW, int C, int bps) {
 // (measured in round 1: asking for the GEMM kernels' maximum shared-memory carveout here made the step 1.4 % slower —
 // the streaming kernels do profit from L1 — so no carveout preference is set)
 int gn_make_ab(const double* sums, const void* gamma, const void* beta, int pdt, float eps, int N, int HW, int C, int G,
-               float* ab, cudaStream_t st) {
+               float* ab, float* zero_dsdb, cudaStream_t st) {
   if (check_shape(C, G)) return -1;
-  gn_ab_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, gamma, beta, pdt, eps, N, HW, C, G, ab);
+  gn_ab_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, gamma, beta, pdt, eps, N, HW, C, G, ab, zero_dsdb);
   VCD_LAUNCH_CHECK();
   return 0;
 }
@@ -601,9 +604,12 @@ static size_t stats_smem(int K, int C) {   // cp.async staging, reused for the [
 
 extern "C" int vcd_gn_stats(const void* x, double* sums, float* chan_stats_in, float near_zero, int N, int HW, int C,
                             int G, vcd_stream_t stream) {
+  return gn_stats_launch(x, sums, chan_stats_in, near_zero, N, HW, C, G, as_stream(stream), false);
+}
+int gn_stats_launch(const void* x, double* sums, float* chan_stats_in, float near_zero, int N, int HW, int C, int G,
+                    cudaStream_t st, bool prezeroed) {
   if (check_shape(C, G)) return -1;
-  cudaStream_t st = as_stream(stream);
-  VCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * G, st));
+  if (!prezeroed) VCD_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * N * G, st));
   const GnShape sh = gn_launch_shape(N, HW, C, chan_stats_in ? 2 : 3);
   if (chan_stats_in && near_zero > 0.f)
     gn_stats_kernel<true, true><<<sh.grid, kThreads, stats_smem(5, C), st>>>(
@@ -659,7 +665,9 @@ extern "C" int vcd_gn_bwd_reduce(const void* x, const void* dout, const double* 
                                  vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
-  VCD_CUDA(cudaMemsetAsync(dsdb, 0, sizeof(float) * 2 * N * C, st));
+  const bool prezeroed = (act_silu & VCD_ACC_PREZEROED) != 0;
+  act_silu &= 1;
+  if (!prezeroed) VCD_CUDA(cudaMemsetAsync(dsdb, 0, sizeof(float) * 2 * N * C, st));
   const GnShape sh = gn_launch_shape(N, HW, C, 3);
   const size_t smem = Pipe<2, 2, kReduceStages>::kBytes;   // >= the [2][8][kThreads] floats of the final reduction
   VCD_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -680,7 +688,9 @@ extern "C" int vcd_gn_bwd_apply(const void* x, const void* dout, const double* s
                                 vcd_stream_t stream) {
   if (check_shape(C, G)) return -1;
   cudaStream_t st = as_stream(stream);
-  if (dx_colsum) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
+  const bool prezeroed = (act_silu & VCD_ACC_PREZEROED) != 0;
+  act_silu &= 1;
+  if (dx_colsum && !prezeroed) VCD_CUDA(cudaMemsetAsync(dx_colsum, 0, sizeof(float) * C, st));
   const size_t smem = dres ? Pipe<3, 2, kApplyBwdStagesRes>::kBytes : Pipe<2, 2, kApplyBwdStages>::kBytes;   // >= 8 * kThreads floats
   const GnShape sh = gn_launch_shape(N, HW, C, 3);
   const bool wide = ((C / G) & 3) == 0;

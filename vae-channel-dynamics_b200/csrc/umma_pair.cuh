@@ -71,13 +71,14 @@ struct GnEpilogue {
   int groups;
   bool fused;    // set by the launcher: the kernel produced the sums
   bool accumulate = false;  // add to sums already started by an earlier launch (phase convolutions): no zeroing
+  bool prezeroed = false;   // the caller guarantees sums is zero (VCD_ACC_PREZEROED): no zeroing
 };
 
 // fused GroupNorm backward prologue of a dgrad launch (host side)
 struct GnBwdPrologue {
   const void* x;
   const float* ab;
-  float* dsdb;
+  float* dsdb;   // zeroed by the kernel that writes ab (gn_make_ab)
   int act;
 };
 

@@ -76,6 +76,54 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------
+# zero-filled accumulator arenas
+# ------------------------------------------------------------------------------------------
+class _ZeroPool:
+    """Buffers that kernels ADD into (GroupNorm sums from the GEMM epilogues, backward sums, bias-gradient column sums,
+    split-K weight-gradient workspaces) are carved out of zero-filled chunks and handed to the entry points with
+    VCD_ACC_PREZEROED, instead of being zeroed one by one inside every call: a training step at 512^2 issued 246 memsets —
+    2 us of device time plus one more launch boundary each (measured: ~1 ms per step) — and now issues ~25 memsets and a
+    handful of chunk fills.
+
+    A chunk is an ordinary caching-allocator tensor, filled once (`torch.zeros`) on the stream that uses it; every slice
+    is handed out exactly once and keeps the chunk alive, so lifetimes need no bookkeeping (forward sums live until their
+    backward, a retained graph keeps its chunk).  Chunks are per (device, stream): the weight-gradient side stream owns
+    its own.  Inside a CUDA-graph capture the pool is bypassed (a chunk must not straddle the capture boundary)."""
+
+    def __init__(self, chunk_bytes: int):
+        self.chunk_bytes = chunk_bytes
+        self.cur = {}     # (device, raw stream) -> [chunk, offset]
+
+    def take(self, numel: int, dtype: torch.dtype, device):
+        """-> (tensor, VCD_ACC_PREZEROED) out of the arena, or (uninitialised tensor, 0) when it does not apply"""
+        nbytes = numel * _ITEMSIZE[dtype]
+        need = (nbytes + 255) & ~255
+        if not zero_pool_enabled or need > self.chunk_bytes or torch._C._cuda_isCurrentStreamCapturing():
+            return torch.empty(numel, dtype=dtype, device=device), 0
+        key = (torch._C._cuda_getDevice(), _st())
+        e = self.cur.get(key)
+        if e is None or e[1] + need > self.chunk_bytes:
+            e = self.cur[key] = [torch.zeros(self.chunk_bytes, dtype=torch.uint8, device=device), 0]
+        off = e[1]
+        e[1] = off + need
+        return e[0][off:off + nbytes].view(dtype), _lib.ACC_PREZEROED
+
+    def reset(self) -> None:
+        self.cur.clear()
+
+
+_ITEMSIZE = {torch.float32: 4, torch.float64: 8}
+zero_pool_enabled = __import__("os").environ.get("VCD_ZERO_POOL", "1") == "1"
+_acc_pool = _ZeroPool(2 << 20)       # sums [N][G][2] fp64, dsdb [N][C][2] fp32, column sums [C] fp32: ~1.5 MB per step at B=8
+_ws_pool = _ZeroPool(96 << 20)       # fp32 [taps][Cout][Cin] split-K accumulators (<= 9.4 MB per layer, 336 MB per step)
+
+
+def zero_pool_reset() -> None:
+    _acc_pool.reset()
+    _ws_pool.reset()
+
+
+# ------------------------------------------------------------------------------------------
 # statistics slots (device side of ActivityMonitor; SURVEY B.1)
 # ------------------------------------------------------------------------------------------
 class TrackSlot:
@@ -345,9 +393,9 @@ class _ConvFn(torch.autograd.Function):
             residual = _nhwc(residual)
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
         ws = _workspace("vcd_conv2d_fprop_ws_bytes", (N, H, W, Cin, Cout, KH, KW, stride), impl, x.device)
-        sums = torch.empty(N * gn_groups * 2, dtype=torch.float64, device=x.device) if gn_groups else None
+        sums, zf = _acc_pool.take(N * gn_groups * 2, torch.float64, x.device) if gn_groups else (None, 0)
         call("vcd_conv2d_fprop", _p(xs), _p(wf), _p(b32), _p(residual), _p(y), _p(ws), N, H, W, Cin, Cout, KH, KW, stride,
-             pad_t, pad_l, Ho, Wo, planes, impl, _p(sums), gn_groups, _st())
+             pad_t, pad_l, Ho, Wo, planes, impl | zf, _p(sums), gn_groups, _st())
         if sums is not None:
             push_gn_sums(y, sums, gn_groups)
         # x = act(GroupNorm(.)) with this conv as its only consumer: the dgrad epilogue will do the GroupNorm's reduction
@@ -408,25 +456,27 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def _wgrad_alloc(ctx, dy, weight, bias, prepare=True):
+        """-> (dw, db, ws, flags): ws out of the zero-filled arena (flags = VCD_ACC_PREZEROED) when it fits a chunk;
+        prepare: otherwise zero it now (the programmatic-dependent-launch path needs it zero BEFORE the dgrad kernel)"""
         N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl = ctx.cfg
         dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
         db = None if bias is None else torch.empty_like(bias)
         nbytes = _lib.lib().vcd_conv2d_wgrad_ws_bytes(N, H, W, Cin, Cout, KH, KW, stride)
-        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
-        if prepare:
+        ws, zf = _ws_pool.take(nbytes // 4, torch.float32, dy.device)
+        if prepare and not zf:
             call("vcd_conv2d_wgrad_prepare", _p(ws), Cin, Cout, KH, KW, _st())
-        return dw, db, ws
+        return dw, db, ws, zf
 
     @staticmethod
     def _wgrad(ctx, xs, dy, weight, bias, prepared=None):
         """prepared = (dw, db, ws) of _wgrad_alloc issued BEFORE the dgrad kernel that directly precedes this call in the
         stream: the GEMM is launched with VCD_WGRAD_OVERLAP_PREV and starts while that kernel's last wave drains."""
         N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl = ctx.cfg
-        dw, db, ws = prepared if prepared is not None else _ConvFn._wgrad_alloc(ctx, dy, weight, bias, prepare=False)
+        dw, db, ws, zf = prepared if prepared is not None else _ConvFn._wgrad_alloc(ctx, dy, weight, bias, prepare=False)
         colsum = pop_colsum(dy) if db is not None else None
         call("vcd_conv2d_wgrad", _p(xs), _p(dy), _p(dw), _p(db), _p(colsum), dtype_code(weight), _p(ws), N, H, W, Cin, Cout,
-             KH, KW, stride, pad_t, pad_l, Ho, Wo, planes, impl | (_lib.WGRAD_OVERLAP_PREV if prepared is not None else 0),
-             _st())
+             KH, KW, stride, pad_t, pad_l, Ho, Wo, planes,
+             impl | zf | (_lib.WGRAD_OVERLAP_PREV if prepared is not None else 0), _st())
         return dw, db, colsum
 
 
@@ -587,16 +637,16 @@ class _GroupNormFn(torch.autograd.Function):
             # dout is already g = dL/d(pre-activation) and its channel sums were reduced by the conv's dgrad epilogue
             dsdb, act = fused[1], 0
         else:
-            dsdb = torch.empty(N * C * 2, dtype=torch.float32, device=x.device)
-            call("vcd_gn_bwd_reduce", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), eps, act, N, hw, C, G, _st())
+            dsdb, zf = _acc_pool.take(N * C * 2, torch.float32, x.device)
+            call("vcd_gn_bwd_reduce", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), eps, act | zf, N, hw, C, G, _st())
         dx = None
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(beta)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            colsum = torch.empty(C, dtype=torch.float32, device=x.device)
+            colsum, zf = _acc_pool.take(C, torch.float32, x.device)
             call("vcd_gn_bwd_apply", _p(x), _p(dout), _p(sums), _p(g), _p(b), pdt, _p(dsdb), _p(dx), _p(dres),
-                 _p(colsum), _p(dgamma), _p(dbeta), eps, act, N, hw, C, G, _st())   # also writes dgamma / dbeta
+                 _p(colsum), _p(dgamma), _p(dbeta), eps, act | zf, N, hw, C, G, _st())   # also writes dgamma / dbeta
             push_colsum(dx, colsum)
         else:
             call("vcd_gn_param_grad", _p(sums), _p(dsdb), _p(dgamma), _p(dbeta), pdt, eps, N, hw, C, G, _st())
