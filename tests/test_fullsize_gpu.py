@@ -48,7 +48,9 @@ def test_pair_and_single_cta_kernels_agree_at_full_size(vcd, N, H, cin, cout, k,
 
     y1, dx1, dw1, db1, used1 = run(1)
     y0, dx0, dw0, db0, used0 = run(0)
-    assert used1 >= 2 and used0 == 0
+    # decoder.conv_out with VCD_SMALL_CONV=1: only the narrow-N fprop is a pair-kernel launch (its 3 -> 128 data gradient
+    # then runs in conv_small.cu)
+    assert used1 >= (1 if cout < 8 else 2) and used0 == 0
     # same bf16 inputs, fp32 accumulation in a different order: at most ~1 bf16 ulp (2^-8) of the largest element
     assert rel_err(y1, y0) < 8e-3
     assert rel_err(dx1, dx0) < 8e-3

@@ -176,6 +176,7 @@ def test_five_optimizer_steps_track_the_oracle(vcd, monkeypatch):
     gammas equal up to the optimizer's own per-step update (losses: median < 5e-3, every step < 2e-2)."""
     from oracle.torch_vae import oracle_forward, oracle_losses
     from oracle import components as oc
+    vcd.add_src_to_path()
     from tracking.monitor import ActivityMonitor
     from classification.classifier import RegionClassifier
     from intervention.nudger import InterventionHandler

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libvcd_b200.so")
-SOURCES = ["conv_dispatch.cu", "umma_gemm.cu", "umma_pair.cu", "conv_simt.cu", "gn.cu", "elementwise.cu", "tracker.cu", "metrics.cu", "optimizer.cu"]
+SOURCES = ["conv_dispatch.cu", "umma_gemm.cu", "umma_pair.cu", "conv_simt.cu", "conv_small.cu", "gn.cu", "elementwise.cu", "tracker.cu", "metrics.cu", "optimizer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

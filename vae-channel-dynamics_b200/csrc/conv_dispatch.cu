@@ -408,27 +408,27 @@ int umma_wgrad(const void* x, const void* dy, float* ws, int N, int H, int W, in
 // ---------------------------------------------------------------- small-channel layers on the GEMM kernel
 // patch[px][col], col = t*S + s  ->  src[n, h + dh[t], w + dw[t], s]   (zero outside the image / beyond taps*S)
 struct PatchTaps { int n; int dh[9], dw[9]; };
-// One block = 64 consecutive pixels of one image row.  The three source rows (h-1 .. h+1, 66 pixels each, zero outside
-// the image) are staged in shared memory with coalesced loads, every patch column's source offset comes from a small
-// table (no per-element division), and each thread writes whole 16-byte vectors: the kernel runs at the rate the patch
-// can be WRITTEN (round 1's per-element gather issued eight scattered 2-byte loads and eight divisions per vector:
-// 0.27 ms per 512^2 patch, four of them per step).
-constexpr int kI2cPx = 64;
+// One block = 4 image rows x 64 consecutive pixels.  The six source rows (h0-1 .. h0+4, 66 pixels each, zero outside the
+// image) are staged in shared memory with coalesced loads, every patch column's source offset comes from a small table
+// (no per-element division), and each thread writes whole 16-byte vectors: the kernel runs at the rate the patch can be
+// WRITTEN (round 1's per-element gather issued eight scattered 2-byte loads and eight divisions per vector: 0.27 ms per
+// 512^2 patch, four of them per step; one image row per block kept only 8 KB of stores in flight per block: 0.12-0.24 ms).
+constexpr int kI2cPx = 64, kI2cRows = 4;
 __global__ void __launch_bounds__(256) im2col_small_kernel(const bf16* __restrict__ src, bf16* __restrict__ patch, int N,
                                                            int H, int W, int S, int Kp, PatchTaps taps) {
   extern __shared__ unsigned char i2c_smem[];
-  bf16* rows = reinterpret_cast<bf16*>(i2c_smem);                 // [3][kI2cPx + 2][S]
-  short* off = reinterpret_cast<short*>(rows + 3 * (kI2cPx + 2) * S);   // [Kp]: offset into rows relative to the pixel, -1 = zero
-  const int segs = (W + kI2cPx - 1) / kI2cPx;
+  bf16* rows = reinterpret_cast<bf16*>(i2c_smem);                                   // [kI2cRows + 2][kI2cPx + 2][S]
+  short* off = reinterpret_cast<short*>(rows + (kI2cRows + 2) * (kI2cPx + 2) * S);  // [Kp]: offset relative to the pixel, -1 = zero
+  const int segs = (W + kI2cPx - 1) / kI2cPx, hblocks = (H + kI2cRows - 1) / kI2cRows;
   const int seg = blockIdx.x % segs;
-  const int64_t row = blockIdx.x / segs;       // n * H + h
-  const int h = (int)(row % H);
-  const int64_t n = row / H;
+  const int t0 = blockIdx.x / segs;
+  const int h0 = (t0 % hblocks) * kI2cRows;
+  const int64_t n = t0 / hblocks;
   const int w0 = seg * kI2cPx;
   const int RW = (kI2cPx + 2) * S;
-  for (int i = threadIdx.x; i < 3 * RW; i += blockDim.x) {
+  for (int i = threadIdx.x; i < (kI2cRows + 2) * RW; i += blockDim.x) {
     const int r = i / RW, e = i - r * RW;
-    const int wi = w0 - 1 + e / S, hi = h - 1 + r;
+    const int wi = w0 - 1 + e / S, hi = h0 - 1 + r;
     bf16 v = __float2bfloat16_rn(0.f);
     if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = src[((n * H + hi) * W + wi) * S + (e % S)];
     rows[i] = v;
@@ -439,27 +439,28 @@ __global__ void __launch_bounds__(256) im2col_small_kernel(const bf16* __restric
   }
   __syncthreads();
   const int V = Kp / 8;
-  const int npx = min(kI2cPx, W - w0);
-  for (int i = threadIdx.x; i < npx * V; i += blockDim.x) {
-    const int v = i % V, px = i / V;
-    const bf16* base = rows + px * S;
+  const int npx = min(kI2cPx, W - w0), nrows = min(kI2cRows, H - h0);
+  for (int i = threadIdx.x; i < nrows * npx * V; i += blockDim.x) {
+    const int v = i % V, q = i / V;
+    const int px = q % npx, r = q / npx;
+    const bf16* base = rows + (r * (kI2cPx + 2) + px) * S;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int o = off[v * 8 + j];
       f[j] = o >= 0 ? __bfloat162float(base[o]) : 0.f;
     }
-    st8(patch + ((row * W + w0 + px) * (int64_t)Kp) + v * 8, pack8(f));
+    st8(patch + (((n * H + h0 + r) * W + w0 + px) * (int64_t)Kp) + v * 8, pack8(f));
   }
 }
 static int im2col_small_launch(const bf16* src, bf16* patch, int N, int H, int W, int S, int Kp, const PatchTaps& taps,
                                cudaStream_t st) {
   for (int t = 0; t < taps.n; ++t)
     VCD_CHECK_ARG(taps.dh[t] >= -1 && taps.dh[t] <= 1 && taps.dw[t] >= -1 && taps.dw[t] <= 1, "im2col: taps beyond 3x3");
-  const int segs = (W + kI2cPx - 1) / kI2cPx;
-  const int64_t blocks = (int64_t)N * H * segs;
+  const int segs = (W + kI2cPx - 1) / kI2cPx, hblocks = (H + kI2cRows - 1) / kI2cRows;
+  const int64_t blocks = (int64_t)N * hblocks * segs;
   VCD_CHECK_ARG(blocks < (1ll << 31), "im2col: too many rows");
-  const size_t smem = (size_t)3 * (kI2cPx + 2) * S * sizeof(bf16) + (size_t)Kp * sizeof(short);
+  const size_t smem = (size_t)(kI2cRows + 2) * (kI2cPx + 2) * S * sizeof(bf16) + (size_t)Kp * sizeof(short);
   im2col_small_kernel<<<(unsigned)blocks, 256, smem, st>>>(src, patch, N, H, W, S, Kp, taps);
   VCD_LAUNCH_CHECK();
   return 0;
@@ -875,10 +876,12 @@ static int wgrad_path(int Cin, int Cout, int KH, int KW, int stride) {
 }
 
 extern "C" int64_t vcd_conv2d_fprop_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
-  return fprop_path(Cin, Cout, KH, KW, stride) == 4 ? patch_gemm_ws((int64_t)N * H * W, Cin, Cout, KH * KW) : 0;
+  if (fprop_path(Cin, Cout, KH, KW, stride) != 4 || small_in_conv_ok(Cin, Cout, KH, KW, stride)) return 0;
+  return patch_gemm_ws((int64_t)N * H * W, Cin, Cout, KH * KW);
 }
 extern "C" int64_t vcd_conv2d_dgrad_ws_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
-  return dgrad_path(Cin, Cout, KH, KW, stride) == 4 ? patch_gemm_ws((int64_t)N * H * W, Cout, Cin, KH * KW) : 0;
+  if (dgrad_path(Cin, Cout, KH, KW, stride) != 4 || small_in_conv_ok(Cout, Cin, KH, KW, stride)) return 0;
+  return patch_gemm_ws((int64_t)N * H * W, Cout, Cin, KH * KW);
 }
 
 static int conv_fprop_impl(const void* x, const void* w_fprop, const float* bias, const void* residual, void* y, void* ws,
@@ -916,6 +919,8 @@ static int conv_fprop_impl(const void* x, const void* w_fprop, const float* bias
   VCD_CHECK_ARG(!x_planes, "conv fprop: parity-plane input only on the tcgen05 stride-2 path");
   if (path == 3 && !residual)
     return narrow_conv(x, w_fprop, bias, y, N, H, W, Cin, Cout, KH, KW, pad_t, pad_l, +1, st);
+  if (path == 4 && !residual && small_in_conv_ok(Cin, Cout, KH, KW, stride))     // conv_in: patch only in shared memory
+    return small_in_conv_launch(x, w_fprop, bias, y, N, H, W, Cin, Cout, KH, KW, pad_t, pad_l, +1, st);
   if (path == 4 && !residual)
     return patch_gemm(x, w_fprop, bias, y, ws, N, H, W, Cin, Cout, KH, KW, pad_t, pad_l, +1, st);
   return simt_conv_fprop(x, w_fprop, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, st);
@@ -936,6 +941,8 @@ extern "C" int vcd_conv2d_dgrad(const void* dy, const void* w_fprop, const void*
   VCD_CHECK_ARG(w_dgrad != nullptr, "conv dgrad needs the w_dgrad pack");
   // dx[q][ci] = sum_t sum_co dy[q - (k - pad)][co] * w_dgrad[t][ci][co]
   if (path == 3) return narrow_conv(dy, w_dgrad, nullptr, dx, N, H, W, Cout, Cin, KH, KW, pad_t, pad_l, -1, st);
+  if (path == 4 && small_in_conv_ok(Cout, Cin, KH, KW, stride))                  // conv_out's data gradient
+    return small_in_conv_launch(dy, w_dgrad, nullptr, dx, N, H, W, Cout, Cin, KH, KW, pad_t, pad_l, -1, st);
   if (path == 4) return patch_gemm(dy, w_dgrad, nullptr, dx, ws, N, H, W, Cout, Cin, KH, KW, pad_t, pad_l, -1, st);
   return simt_conv_dgrad(dy, w_dgrad, dx, N, H, W, Cin, Cout, KH, KW, stride, pad_t, pad_l, Ho, Wo, st);
 }

@@ -18,3 +18,7 @@ int gn_make_ab(const double* sums, const void* gamma, const void* beta, int pdt,
 // vcd_gn_stats with the zeroing of `sums` optional (prezeroed: the caller guarantees it is zero)
 int gn_stats_launch(const void* x, double* sums, float* chan_stats_in, float near_zero, int N, int HW, int C, int G,
                     cudaStream_t st, bool prezeroed);
+// conv_small.cu: S <= 8 source channels -> 128 output channels with the im2col patch held in shared memory only
+bool small_in_conv_ok(int S, int O, int KH, int KW, int stride);
+int small_in_conv_launch(const void* src, const void* pack, const float* bias, void* out, int N, int H, int W, int S, int O,
+                         int KH, int KW, int pad_t, int pad_l, int sign, cudaStream_t st);
