@@ -220,3 +220,78 @@ def test_from_pretrained_reads_legacy_sdxl_vae_checkpoints(tmp_path):
     again = load_file(str(out / "diffusion_pytorch_model.safetensors"))
     assert set(again) == set(sd) and all(torch.equal(again[k], sd[k]) for k in sd)
     assert json.loads((out / "config.json").read_text())["block_out_channels"] == [128, 256, 512, 512]
+
+
+def test_zero_pool_hands_out_disjoint_zero_slices_once(vcd, monkeypatch):
+    """Host logic of the zero-filled accumulator arenas (ops._ZeroPool): every slice is zero, 256-byte aligned inside its
+    chunk, handed out exactly once (no two slices overlap), typed as asked; a request that does not fit the current chunk
+    opens a new one while the old chunk stays alive through its slices; oversize requests, a disabled pool and a CUDA-graph
+    capture fall back to an uninitialised tensor WITHOUT the VCD_ACC_PREZEROED flag.  (CPU tensors stand in for device
+    memory; the stream key and the capture query are the two CUDA calls of take().)"""
+    import torch
+    ops, lib = vcd.ops, vcd._lib
+    capturing = {"v": False}
+    monkeypatch.setattr(ops, "_st", lambda: 7)
+    monkeypatch.setattr(torch._C, "_cuda_getDevice", lambda: 0)
+    monkeypatch.setattr(torch._C, "_cuda_isCurrentStreamCapturing", lambda: capturing["v"])
+    monkeypatch.setattr(ops, "zero_pool_enabled", True)
+    pool = ops._ZeroPool(4096)
+    dev = torch.device("cpu")
+    taken = []
+    for numel, dt in ((10, torch.float64), (3, torch.float32), (100, torch.float32), (1, torch.float64)):
+        t, flag = pool.take(numel, dt, dev)
+        assert flag == lib.ACC_PREZEROED and t.dtype == dt and t.numel() == numel and float(t.abs().sum()) == 0.0
+        taken.append(t)
+    chunk0 = pool.cur[(0, 7)][0]
+    base = chunk0.data_ptr()
+    spans = sorted((t.data_ptr() - base, t.data_ptr() - base + t.numel() * t.element_size()) for t in taken)
+    assert all(a % 256 == 0 for a, _ in spans)
+    assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    for t in taken:
+        t.fill_(1.0)                                   # the kernels add into their slices ...
+    t, flag = pool.take(16, torch.float32, dev)        # ... and a later slice is still zero
+    assert flag and float(t.abs().sum()) == 0.0
+    # chunk rollover: 4096-byte chunk, 1280 bytes used so far -> a 3000-byte request opens a fresh chunk
+    big, flag = pool.take(750, torch.float32, dev)
+    assert flag and pool.cur[(0, 7)][0] is not chunk0 and float(big.abs().sum()) == 0.0
+    assert float(taken[0].sum()) == 10.0               # the old chunk lives on through its slices
+    # per-stream chunks
+    monkeypatch.setattr(ops, "_st", lambda: 9)
+    other, flag = pool.take(4, torch.float32, dev)
+    assert flag and (0, 9) in pool.cur and pool.cur[(0, 9)][0] is not pool.cur[(0, 7)][0]
+    # fallbacks: too large for a chunk, capture in progress, pool disabled
+    t, flag = pool.take(2000, torch.float32, dev)
+    assert flag == 0 and t.numel() == 2000
+    capturing["v"] = True
+    t, flag = pool.take(4, torch.float32, dev)
+    assert flag == 0
+    capturing["v"] = False
+    monkeypatch.setattr(ops, "zero_pool_enabled", False)
+    t, flag = pool.take(4, torch.float32, dev)
+    assert flag == 0
+    pool.reset()
+    assert not pool.cur
+
+
+def test_wgrad_overlap_mode_selection(vcd, monkeypatch):
+    """VCD_WGRAD_OVERLAP / VCD_WGRAD_STREAM / the bench's profiling switch select how a conv's weight gradient overlaps its
+    data gradient (ops._wgrad_overlap_mode): side stream by default, programmatic dependent launch or none on request, and
+    none at all while bench.py brackets every call with CUDA events."""
+    ops = vcd.ops
+    monkeypatch.delenv("VCD_WGRAD_OVERLAP", raising=False)
+    monkeypatch.delenv("VCD_WGRAD_STREAM", raising=False)
+    monkeypatch.setattr(ops, "wgrad_side_stream_enabled", True)
+    assert ops._wgrad_overlap_mode() == "stream"
+    monkeypatch.setenv("VCD_WGRAD_OVERLAP", "pdl")
+    assert ops._wgrad_overlap_mode() == "pdl"
+    monkeypatch.setenv("VCD_WGRAD_OVERLAP", "off")
+    assert ops._wgrad_overlap_mode() == "off"
+    monkeypatch.setenv("VCD_WGRAD_OVERLAP", "pdl")
+    monkeypatch.setenv("VCD_WGRAD_STREAM", "0")
+    assert ops._wgrad_overlap_mode() == "off"
+    monkeypatch.delenv("VCD_WGRAD_STREAM")
+    monkeypatch.setattr(ops, "wgrad_side_stream_enabled", False)
+    assert ops._wgrad_overlap_mode() == "off"
+    assert vcd._lib.WGRAD_OVERLAP_PREV == 0x100 and vcd._lib.ACC_PREZEROED == 0x200      # include/vcd.h
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "vcd.h")).read()
+    assert "#define VCD_WGRAD_OVERLAP_PREV 0x100" in hdr and "#define VCD_ACC_PREZEROED 0x200" in hdr
