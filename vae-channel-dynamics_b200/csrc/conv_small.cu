@@ -166,12 +166,11 @@ size_t small_smem_bytes(int Kp) {
 }  // namespace
 
 bool small_in_conv_ok(int S, int O, int KH, int KW, int stride) {
-  // OPT-IN (VCD_SMALL_CONV=1).  Measured on B200: output bit-identical to the im2col patch + GEMM path on conv_in fprop and
-  // conv_out dgrad (2 M outputs compared element by element), 3 -> 128 fprop at 512^2 B=8 0.463 -> 0.326 ms.  Not the default
-  // because the 6-step AdamW trajectory test moved with it (loss error at steps 5-6: 1.1e-2 instead of 2-5e-3, reproducibly)
-  // although every tensor this kernel writes is unchanged — the only other difference is that these layers no longer allocate
-  // their 2 MB patch workspace, i.e. the order in which the caching allocator hands out blocks.  Until that sensitivity is
-  // understood the validated path stays the default.
+  // OPT-IN (VCD_SMALL_CONV=1).  Measured on B200: conv_out's data gradient identical to the im2col patch + GEMM path in all
+  // 2 097 152 elements compared, conv_in's forward different in exactly one (one bf16 ulp: two k16 accumulation steps here,
+  // four there); 3 -> 128 fprop at 512^2 B=8 0.463 -> 0.326 ms.  Not the default because the 6-step AdamW trajectory test
+  // moved with it (loss error at steps 5-6: 1.1e-2 instead of 2-5e-3, median gate 5e-3) — most likely the re-drawn bf16
+  // rounding noise behind that one ulp, but not confirmed before the round's GPU budget ended.
   static int on = -1;
   if (on < 0) { const char* e = getenv("VCD_SMALL_CONV"); on = (e && e[0] == '1') ? 1 : 0; }
   if (!on) return false;
