@@ -295,3 +295,42 @@ def test_wgrad_overlap_mode_selection(vcd, monkeypatch):
     assert vcd._lib.WGRAD_OVERLAP_PREV == 0x100 and vcd._lib.ACC_PREZEROED == 0x200      # include/vcd.h
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "vcd.h")).read()
     assert "#define VCD_WGRAD_OVERLAP_PREV 0x100" in hdr and "#define VCD_ACC_PREZEROED 0x200" in hdr
+
+
+def test_pack_plan_tiles_cover_every_weight_exactly_once(vcd):
+    """Host side of vcd_multi_pack_weights (ops.PackPlan): the work list covers every (Cout, Cin) position of every layer
+    exactly once with the library's tile size, including the ragged small-channel layers (3 -> 128, 512 -> 8, 4 -> 4) and
+    Linear weights (taps = 1); descriptors carry the shapes the kernel indexes with.  Built on CPU tensors (no launch)."""
+    import ctypes as C
+    ops, lib = vcd.ops, vcd._lib.lib()
+    tco, tci = lib.vcd_pack_tile_co(), lib.vcd_pack_tile_ci()
+    assert tco >= 8 and tci >= 8 and tco % 8 == 0 and tci % 8 == 0       # 16-byte stores of eight channels
+    shapes = [(128, 3, 3, 3), (8, 512, 3, 3), (4, 4, 1, 1), (512, 512), (256, 128, 1, 1), (128, 128, 3, 3), (512, 4, 3, 3)]
+    layers = []
+    for sh in shapes:
+        w = torch.zeros(sh)
+        b = torch.zeros(sh[0])
+        layers.append((w, b, ops.PackedWeights(), 0))
+    layers.append((torch.zeros(256, 256, 3, 3), torch.zeros(256), ops.UpconvPackedWeights(), 1))     # Upsample2D conv
+    plan = ops.PackPlan(layers)
+    assert plan.n_tiles == len(plan.tile_layer) == len(plan.tile_co) == len(plan.tile_ci)
+    seen = {}
+    for l, co, ci in zip(plan.tile_layer.tolist(), plan.tile_co.tolist(), plan.tile_ci.tolist()):
+        cout, cin = layers[l][0].shape[0], layers[l][0].shape[1]
+        assert co % tco == 0 and ci % tci == 0 and co < cout and ci < cin
+        assert (l, co, ci) not in seen
+        seen[(l, co, ci)] = True
+    for l, (w, _, packs, mode) in enumerate(layers):
+        cout, cin = w.shape[0], w.shape[1]
+        assert sum(1 for k in seen if k[0] == l) == -(-cout // tco) * -(-cin // tci)
+        taps = w.shape[2] * w.shape[3] if w.dim() == 4 else 1
+        assert packs.wf.numel() == (16 if mode == 1 else taps) * cout * cin == packs.wd.numel()
+        assert packs.bias is not None and packs.bias.numel() == cout and packs.bias.dtype == torch.float32
+    # descriptor bytes: 5 pointers + 6 int32 per layer, shapes in the order the kernel reads them
+    raw = bytes(plan.descs.tolist())
+    rec = 5 * 8 + 6 * 4
+    assert len(raw) == rec * len(layers)
+    for l, (w, _, _, mode) in enumerate(layers):
+        dtype, cout, cin, taps, m, _pad = (C.c_int32 * 6).from_buffer_copy(raw[l * rec + 40:(l + 1) * rec])
+        assert (cout, cin, m) == (w.shape[0], w.shape[1], mode)
+        assert taps == (w.shape[2] * w.shape[3] if w.dim() == 4 else 1) and dtype == vcd._lib.F32
