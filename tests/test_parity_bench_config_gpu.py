@@ -173,7 +173,7 @@ def test_five_optimizer_steps_track_the_oracle(vcd, monkeypatch):
     """Loss / gamma trajectory over 6 optimizer steps (fp32 parameters as in experiment_cifar10_test.yaml) with the same
     AdamW, clip, tracking every 2 steps, classification and nudge (train.py:299-330), against the oracle driven by the
     reference tracker formulas (oracle/components.py): losses within 1e-2, masks and nudge counts identical, nudged
-    gammas equal up to the optimizer's own per-step update (losses: median < 5e-3, every step < 2e-2)."""
+    gammas equal up to the optimizer's own per-step update (losses: median < 5e-3, every step < 2.5e-2)."""
     from oracle.torch_vae import oracle_forward, oracle_losses
     from oracle import components as oc
     vcd.add_src_to_path()
@@ -237,8 +237,11 @@ def test_five_optimizer_steps_track_the_oracle(vcd, monkeypatch):
         "steps": traj, "max_abs_gamma_diff": dg, "max_abs_param_diff": dw, "lr": lr,
         "note": "AdamW's first updates are ~lr*sign(g): a parameter whose tiny gradient flips sign under bf16 rounding "
                 "moves by 2*lr per step, hence the bound steps*2*lr"})
-    # measured: 1e-4 .. 1.4e-2 per step (the steps right after a nudge of 80 planted scales are the largest): gate 2e-2
-    assert all(r["e_loss"] < 2e-2 for r in traj), traj
+    # measured per step: 1.5e-4 .. 5e-3, except step 4 (the first forward after the second nudge of 80 planted scales), which
+    # varies from run to run with the order of the fp32 atomics: 1.05e-2, 1.16e-2, 1.50e-2, 1.53e-2, 1.77e-2 in five runs
+    # -> per-step gate 1.4x the worst; median of the six steps 1.6e-3 .. 2.5e-3 -> 5e-3.  (Both are numbers of ONE rounding-
+    # noise realisation: a single flipped bf16 ulp in conv_in moved steps 5-6 to 1.1e-2)
+    assert all(r["e_loss"] < 2.5e-2 for r in traj), traj
     assert sorted(r["e_loss"] for r in traj)[len(traj) // 2] < 5e-3, traj
     assert dg <= 2.5 * lr * steps and dw <= 2.5 * lr * steps, (dg, dw)
 
