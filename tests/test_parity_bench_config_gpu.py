@@ -163,8 +163,11 @@ def test_three_way_step_at_bench_configuration(vcd, monkeypatch, R, B, params_bf
 # statistics: encoder-side layers 2e-5 (north_star 1e-4 met), decoder.up_blocks.1 (40 bf16 layers deep) 0.8-1.1e-3 [2.7-3.1e-3]
 GATES = {
     # grad_median at 64^2: 2.63e-2 .. 2.77e-2 over the builds of this round (torch's own bf16 path: 2.83e-2) -> 1.2x
-    (64, False): dict(reconstruction=3.2e-2, latent_mean=2.75e-2, grad_median=3.3e-2, grad_max=1.0e-1, cos=0.9996, stats=4.5e-3),
-    (256, True): dict(reconstruction=3.15e-2, latent_mean=1.65e-2, grad_median=8.5e-3, grad_max=6.5e-2, cos=0.99995, stats=1.5e-3),
+    # grad_max at 64^2 (worst of 247 tensors, an extreme-value statistic): 7.7e-2 mid-round, 9.3e-2 on the final build -> 1.25x
+    (64, False): dict(reconstruction=3.2e-2, latent_mean=2.75e-2, grad_median=3.3e-2, grad_max=1.17e-1, cos=0.9996, stats=4.5e-3),
+    # 256^2: latent mean 1.31e-2 mid-round / 1.47e-2 final build, gradient median 6.8e-3 / 7.6e-3 (each build is another
+    # realisation of the bf16 rounding noise; torch's own bf16 path: 2.03e-2 / 9.3e-3) -> 1.25x the final build
+    (256, True): dict(reconstruction=3.15e-2, latent_mean=1.85e-2, grad_median=9.5e-3, grad_max=6.5e-2, cos=0.99995, stats=1.5e-3),
     (512, True): dict(reconstruction=2.7e-2, latent_mean=2.05e-2, grad_median=6.5e-3, grad_max=7.5e-2, cos=0.99997, stats=1.2e-3),
 }
 
